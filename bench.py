@@ -1,0 +1,416 @@
+#!/usr/bin/env python3
+"""Headline benchmark of the B200 HSTU hot path (contract: see the task statement / DESIGN.md section "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload hstu_large|attn]
+
+Workload `hstu_large` (default; BASELINE.json metric "user-seqs/sec HSTU-large L=8192 d=256 bf16"):
+  a 16-layer STU stack, D=256, H=8, dqk=dv=32, bf16, over a synthetic jagged batch of `--batch` user sequences per GPU
+  with Lmax=8192 (lengths ~ U[0.9 Lmax, Lmax), 1..20 targets: the reference bench recipe, hstu_attention_bench.py:194-248).
+  One step = forward + backward of the whole stack + (N>1) NCCL all-reduce of the parameter gradients (one bucket per
+  layer, overlapped with the remaining backward) + fused AdamW step.  value = sequences / second over all ranks.
+Workload `attn`: the reference microbench (B=512, H=4, d in {64,128}, fwd+bwd of hstu_mha only).
+
+`--impl reference` times the CPU port of the reference eager path (oracle/) on the host cores on a bounded sample of
+the same workload (the Python reference itself cannot travel to the GPU box).  Rank 0 only.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hstu_large", choices=["hstu_large", "attn"])
+    ap.add_argument("--batch", type=int, default=16, help="user sequences per GPU per step")
+    ap.add_argument("--lmax", type=int, default=8192)
+    ap.add_argument("--layers", type=int, default=16)
+    ap.add_argument("--attn-dim", type=int, default=128, help="head dim of the attn microbench workload")
+    ap.add_argument("--attn-impl", type=int, default=0, help="0 auto, 1 generic kernels, 2 force tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops_burst=d["bf16_tflops"], tflops_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        clocks, maxc, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                clocks.append(float(r[1]))
+                maxc = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        clocks.sort()
+        med = clocks[len(clocks) // 2] if clocks else None
+        return {"sm_mhz": med, "sm_max_mhz": maxc, "reasons": sorted(reasons), "samples": len(clocks)}
+
+
+def synth_lengths(batch, lmax, device, seed):
+    from generative_recommenders_b200.common import apply_sampling, generate_sparse_seq_len
+
+    torch.manual_seed(seed)
+    lengths = generate_sparse_seq_len(batch, lmax, 0.95, device)
+    lengths = apply_sampling(lengths, 2.0, lmax)
+    nt = torch.randint(1, 21, (batch,), device=device, dtype=lengths.dtype)
+    nt = torch.where(nt > lengths, lengths, nt).to(torch.int32)
+    off = torch.zeros(batch + 1, dtype=torch.int64, device=device)
+    off[1:] = torch.cumsum(lengths, 0)
+    return lengths, nt, off
+
+
+def attn_flops(lengths, heads, dqk, dv):
+    """Reference FLOP model (hstu_attention_bench.py:35-59): causal-halved, 2 FLOP per MAC."""
+    s2 = float((lengths.double() ** 2).sum())
+    f1 = 2.0 * heads * dqk * s2 / 2.0
+    f2 = 2.0 * heads * dv * s2 / 2.0
+    return dict(fwd=f1 + f2, bwd=3 * f1 + 2 * f2)
+
+
+def attn_bytes(lengths, heads, dqk, dv, elt=2):
+    """Algorithmic bytes, every tensor touched once."""
+    rows = float(lengths.double().sum())
+    return dict(fwd=elt * rows * heads * (2 * dqk + 2 * dv), bwd=elt * rows * heads * (4 * dqk + 3 * dv))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from generative_recommenders_b200 import _lib
+    from generative_recommenders_b200.build import build
+    from generative_recommenders_b200.modules.stu import STULayer, STULayerConfig, STUStack
+    from generative_recommenders_b200.ops.hstu_attention import hstu_mha
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if rank == 0:
+        build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    _lib.lib()
+    D, H, dh, layers = 256, 8, 32, args.layers
+    lengths, nt, off = synth_lengths(args.batch, args.lmax, dev, 1001 + rank)
+    L = int(off[-1])
+
+    if args.workload == "hstu_large":
+        torch.manual_seed(7)  # identical initial weights on every rank (DDP broadcast equivalent)
+        stack = STUStack([STULayer(STULayerConfig(embedding_dim=D, num_heads=H, hidden_dim=dh, attention_dim=dh,
+                                                  output_dropout_ratio=0.2, target_aware=True, recompute_normed_x=True,
+                                                  recompute_uvqk=True, recompute_y=True, sort_by_length=True))
+                          for _ in range(layers)]).to(dev).to(torch.bfloat16)
+        params = [p for p in stack.parameters()]
+        opt = torch.optim.AdamW(params, lr=1e-4, fused=True)
+        x_dev = torch.randn(L, D, device=dev, dtype=torch.bfloat16)
+        # e2e: the step's inputs live in pinned host memory and are copied in every step
+        x_host = x_dev.cpu().pin_memory()
+        off_host, nt_host, len_host = off.cpu().pin_memory(), nt.cpu().pin_memory(), lengths.cpu().pin_memory()
+        h2d_bytes = x_host.numel() * 2 + off_host.numel() * 8 + nt_host.numel() * 4 + len_host.numel() * 4
+        comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+        pending = []
+
+        if world > 1:  # one flat all-reduce per STU layer, launched as soon as that layer's grads are final
+            for layer in stack._stu_layers:
+                lp = list(layer.parameters())
+                state = {"left": len(lp)}
+
+                def hook(_p, lp=lp, state=state):
+                    state["left"] -= 1
+                    if state["left"] == 0:
+                        state["left"] = len(lp)
+                        ready = torch.cuda.Event()
+                        ready.record(torch.cuda.current_stream(dev))
+                        with torch.cuda.stream(comm_stream):
+                            comm_stream.wait_event(ready)
+                            flat = torch.cat([q.grad.reshape(-1) for q in lp]).float()
+                            dist.all_reduce(flat)
+                            flat.div_(world)
+                            o = 0
+                            for q in lp:
+                                n = q.numel()
+                                q.grad.copy_(flat[o:o + n].view_as(q.grad))
+                                o += n
+                        pending.append(flat)
+
+                for q in lp:
+                    q.register_post_accumulate_grad_hook(hook)
+
+        def step(e2e: bool):
+            if e2e:
+                x = x_host.to(dev, non_blocking=True)
+                o_ = off_host.to(dev, non_blocking=True)
+                n_ = nt_host.to(dev, non_blocking=True)
+                l_ = len_host.to(dev, non_blocking=True)
+            else:
+                x, o_, n_, l_ = x_dev, off, nt, lengths
+            opt.zero_grad(set_to_none=True)
+            y = stack(x=x, x_lengths=l_, x_offsets=o_, max_seq_len=args.lmax, num_targets=n_)
+            loss = y.float().square().mean()
+            loss.backward()
+            if world > 1:
+                torch.cuda.current_stream(dev).wait_stream(comm_stream)
+                pending.clear()
+            opt.step()
+            if e2e:
+                return float(loss.item())  # device -> host read of the step result
+            return loss
+
+        units_per_step = args.batch
+        d2h_bytes = 4
+        cfg = {"workload": f"HSTU-large stack fwd+bwd+AdamW: {layers} layers, D=256, H=8, dqk=dv=32, bf16, Lmax={args.lmax}, "
+                           f"{args.batch} user sequences/GPU (lengths U[0.9,1.0)*Lmax, 1-20 targets, seed 1001+rank), dropout 0.2",
+               "global_batch": args.batch * world, "seq_len": args.lmax, "rows_per_gpu": L,
+               "parallelism": f"dp{world} (batch-sharded, per-layer NCCL all-reduce of grads overlapped with backward)",
+               "l2": f"inputs + activations per step ({L * D * 2 * 6 / 1e6:.0f} MB+) exceed the 126 MB L2; no explicit flush"}
+        aflops = attn_flops(lengths, H, dh, dh)
+        abytes = attn_bytes(lengths, H, dh, dh)
+        per_step_calls = layers
+    else:
+        d = args.attn_dim
+        Ha = 4
+        x = torch.empty(L, Ha, 3 * d, device=dev, dtype=torch.bfloat16).uniform_(-0.01, 0.01)
+        q, k, v = torch.split(x, [d, d, d], dim=-1)
+        q.requires_grad_(True), k.requires_grad_(True), v.requires_grad_(True)
+        alpha = 1.0 / d
+        do = torch.randn(L, Ha, d, device=dev, dtype=torch.bfloat16)
+        x_host = x.detach().cpu().pin_memory()
+        h2d_bytes = x_host.numel() * 2
+
+        def step(e2e: bool):
+            if e2e:
+                xx = x_host.to(dev, non_blocking=True)
+                qq, kk, vv = torch.split(xx, [d, d, d], dim=-1)
+                qq.requires_grad_(True), kk.requires_grad_(True), vv.requires_grad_(True)
+            else:
+                qq, kk, vv = q, k, v
+                q.grad = k.grad = v.grad = None
+            o = hstu_mha(args.lmax, alpha, qq, kk, vv, off, num_targets=nt, sort_by_length=True, impl=args.attn_impl)
+            o.backward(do)
+            if e2e:
+                return float(o[0, 0, 0].item())
+            return o
+
+        units_per_step = args.batch
+        d2h_bytes = 2
+        cfg = {"workload": f"hstu_mha fwd+bwd microbench (hstu_attention_bench.py recipe): B={args.batch}, H=4, d={d}, "
+                           f"Lmax={args.lmax}, bf16, alpha=1/d, targets<=20", "global_batch": args.batch * world,
+               "seq_len": args.lmax, "rows_per_gpu": L, "parallelism": f"dp{world} (independent shards)",
+               "l2": f"q,k,v,o,grads = {L * Ha * d * 2 * 11 / 1e6:.0f} MB per step > 126 MB L2" }
+        aflops = attn_flops(lengths, Ha, d, d)
+        abytes = attn_bytes(lengths, Ha, d, d)
+        per_step_calls = 1
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed_run(e2e: bool, steps: int, warmup: int, with_kernel_timing: bool):
+        for _ in range(warmup):
+            step(e2e)
+        sync_all()
+        _lib.enable_timing(with_kernel_timing)
+        launches0 = _lib.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(e2e)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        events = _lib.timed_events()
+        _lib.enable_timing(False)
+        return ms, _lib.LAUNCHES - launches0, events
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, events = timed_run(False, args.steps, args.warmup, True)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _, _ = timed_run(True, args.steps, 1, False)
+
+    value = units_per_step * world * args.steps / (ms * 1e-3)
+    value_e2e = units_per_step * world * args.steps / (ms_e2e * 1e-3)
+    peaks = measured_peaks()
+    kt = {}
+    for name, evs in (events or {}).items():
+        kt[name] = sum(a.elapsed_time(b) for a, b in evs) / max(1, len(evs))  # ms per call
+    out = {
+        "metric": "user-seqs/sec HSTU-large L=8192 d=256 bf16 fwd+bwd" if args.workload == "hstu_large" else
+                  "user-seqs/sec hstu_mha fwd+bwd microbench",
+        "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": cfg,
+        "e2e": {"value": value_e2e, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if "attn_bwd" in kt and "attn_fwd" in kt:
+        tf_b = aflops["bwd"] / (kt["attn_bwd"] * 1e-3) / 1e12
+        tf_f = aflops["fwd"] / (kt["attn_fwd"] * 1e-3) / 1e12
+        peak = peaks["tflops_sustained"]
+        out["roofline"] = {
+            "kernel": "hstu_attn_bwd (dK/dV + dQ kernels of one layer call)", "bound": "tensor", "achieved": tf_b, "peak": peak,
+            "unit": "TFLOP/s", "frac": tf_b / peak, "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+            "ms_per_launch": kt["attn_bwd"], "algorithmic_flops_per_launch": aflops["bwd"],
+            "fwd": {"achieved": tf_f, "frac": tf_f / peak, "ms_per_launch": kt["attn_fwd"],
+                    "algorithmic_flops_per_launch": aflops["fwd"],
+                    "hbm_gbs_algorithmic": abytes["fwd"] / (kt["attn_fwd"] * 1e-3) / 1e9},
+            "bwd_hbm_gbs_algorithmic": abytes["bwd"] / (kt["attn_bwd"] * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
+            "attn_share_of_step": (kt["attn_bwd"] + kt["attn_fwd"]) * per_step_calls / (ms / args.steps),
+        }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, seconds_budget=20.0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference eager path on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_sample(args, layers_sampled: int):
+    """One sequence (the first of the seeded batch), `layers_sampled` independent STU layers fwd+bwd in fp32 on CPU.
+    Returns seconds."""
+    from oracle import hstu_oracle as O
+
+    dev = torch.device("cpu")
+    D, H, dh = 256, 8, 32
+    torch.manual_seed(1001)
+    lmax = args.lmax
+    length = int(torch.randint(int(0.9 * lmax), lmax, (1,)).item())
+    off = torch.tensor([0, length], dtype=torch.int64)
+    nt = torch.tensor([7], dtype=torch.int64)
+    x = torch.randn(length, D, device=dev)
+    Wd = 4 * H * dh
+    params = {"_input_norm_weight": torch.ones(D), "_input_norm_bias": torch.zeros(D),
+              "_uvqk_weight": torch.randn(D, Wd) * 0.05, "_uvqk_beta": torch.zeros(Wd),
+              "_output_norm_weight": torch.ones(H * dh), "_output_norm_bias": torch.zeros(H * dh),
+              "_output_weight": torch.randn(3 * H * dh, D) * 0.05}
+    t0 = time.perf_counter()
+    for _ in range(layers_sampled):
+        O.stu_layer_fwd_bwd_timed(x, off, lmax, nt, params, H, dh, dh)
+    return time.perf_counter() - t0, length
+
+
+def cpu_baseline(args, seconds_budget: float):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if args.workload != "hstu_large":
+        return {"value": None, "unit": "sequences/s", "cores": cores, "kind": "port", "sample": "not measured for this workload"}
+    t1, length = cpu_sample(args, 1)  # also the warm-up
+    n = max(1, min(args.layers, int(seconds_budget / max(t1, 1e-3))))
+    t, _ = cpu_sample(args, n)
+    per_seq = t / n * args.layers
+    return {"value": 1.0 / per_seq, "unit": "sequences/s", "cores": cores, "kind": "port",
+            "sample": f"oracle (fp32 CPU port of the reference eager path), 1 user sequence of length {length}, {n} of "
+                      f"{args.layers} STU layers fwd+bwd in {t:.1f} s, scaled x{args.layers / n:.1f} to the full stack"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    layers_per_step = 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(args, layers_per_step)
+    t0 = time.perf_counter()
+    length = 0
+    for _ in range(args.steps):
+        _, length = cpu_sample(args, layers_per_step)
+    dt = time.perf_counter() - t0
+    per_seq = dt / args.steps / layers_per_step * args.layers
+    value = 1.0 / per_seq
+    out = {
+        "impl": "reference", "metric": "user-seqs/sec HSTU-large L=8192 d=256 bf16 fwd+bwd", "value": value,
+        "unit": "sequences/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"HSTU-large stack fwd+bwd: {args.layers} layers, D=256, H=8, dqk=dv=32, Lmax={args.lmax} "
+                               "(CPU port of the reference eager path; each step = 1 sequence x 1 layer, scaled to the stack)"},
+        "cpu_baseline": {"value": value, "unit": "sequences/s", "cores": cores, "kind": "port",
+                         "sample": f"1 user sequence (length {length}) x {layers_per_step} STU layer fwd+bwd per step, fp32, "
+                                   f"{cores} threads; scaled x{args.layers} layers"},
+        "e2e": {"value": value, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

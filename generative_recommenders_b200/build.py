@@ -1,0 +1,80 @@
+"""In-tree build of libhstu_b200.so (sm_100a only).
+
+    python -m generative_recommenders_b200.build [--force]
+
+Each translation unit under csrc/ is compiled with
+    nvcc -std=c++20 -gencode arch=compute_100a,code=sm_100a -lineinfo -O3
+and linked into generative_recommenders_b200/lib/libhstu_b200.so (git-ignored; it travels to the GPU box with the
+repo snapshot).  nvcc cross-compiles without a GPU, so this is also the "does it build" check of __graft_entry__.build().
+"""
+import concurrent.futures
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(ROOT, "build", "hstu_b200")
+LIB = os.path.join(HERE, "lib", "libhstu_b200.so")
+
+SOURCES = ["api.cu", "attn_generic.cu", "attn_umma_fwd.cu", "attn_umma_bwd.cu", "umma_selftest.cu", "tmap.cu", "norm.cu", "jagged.cu"]
+NVCC_FLAGS = [
+    "-std=c++20", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcudafe", "--diag_suppress=177",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _deps_mtime() -> float:
+    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "hstu_b200.h"), __file__]
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def is_fresh() -> bool:
+    return os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime()
+
+
+def _compile(src: str, extra) -> str:
+    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    hdrs.append(os.path.join(ROOT, "include", "hstu_b200.h"))
+    newest = max(os.path.getmtime(p) for p in hdrs + [os.path.join(CSRC, src), __file__])
+    if os.path.exists(obj) and os.path.getmtime(obj) >= newest:
+        return obj
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    if r.stderr.strip():
+        sys.stderr.write(r.stderr)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and is_fresh():
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    if force:
+        for f in os.listdir(OBJ):
+            os.remove(os.path.join(OBJ, f))
+    extra = ["-Xptxas", "-v"] if verbose else []
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, extra), SOURCES))
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

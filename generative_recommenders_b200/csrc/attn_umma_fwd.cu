@@ -1,0 +1,328 @@
+// Jagged HSTU attention forward on the 5th-gen tensor cores (tcgen05 + TMEM) with TMA-staged tiles.  bf16 / fp16,
+// dqk == dv in {32, 64, 128}.
+//
+// One CTA per (128-row query tile, head, sequence); heavy (late) query tiles are scheduled first.  Warp roles:
+//   warp 0  lane 0 : TMA producer for Q (once) and the K tiles          (2-stage ring, mbarrier full/empty)
+//   warp 3  lane 0 : TMA producer for the V tiles                      (2-stage ring)
+//   warp 1  lane 0 : tcgen05.mma issuer:  S_t = Q K_t^T  (SS, both K-major)  and  O += P_t V_t  (A = P in smem,
+//                    B = V MN-major), S double-buffered in TMEM, O accumulated in TMEM across all key tiles
+//   warp 2         : TMEM allocation / release
+//   warps 4-7, 8-11: two "silu" warpgroups.  Warpgroup g owns key tiles t = g, g+2, ...: tcgen05.ld S (one query row per
+//                    thread), p = silu(alpha*s) * mask via one MUFU (tanh) + 2 FMA-pipe ops, packs bf16 pairs and writes
+//                    them 16 B at a time into the 128B-swizzled K-major P tile that feeds the second MMA.
+// The 1/N factor of the reference is applied once in the epilogue (O tile: TMEM -> registers -> 128-bit global stores,
+// rows past the sequence end are not written).  Rows of neighbouring sequences that a 128-row TMA box drags in are
+// neutralised by the mask (P = 0 for key positions >= len), never by re-reading memory.
+//
+// Reference semantics: ops/pytorch/pt_hstu_attention.py:130-171; tile skipping mirrors the idea of
+// ops/triton/triton_hstu_attention.py:517-543 (loop bounds from the mask) but is derived from common.cuh's ranges.
+#include "common.cuh"
+#include "internal.h"
+#include "umma.cuh"
+
+namespace hstu {
+using namespace umma;
+
+struct alignas(64) FwdParams {
+  CUtensorMap tmQ, tmK, tmV;
+  const void* seq_offsets;
+  const void* num_targets;
+  void* out;
+  long long o_row_stride, o_head_stride;
+  int offsets_i64, targets_i64;
+  int max_seq_len;
+  int win, min_full, ctx;
+  float alpha_half;  // alpha / 2
+  float inv_n;       // 1 / max_seq_len
+};
+
+template <int D>
+struct FwdCfg {
+  static constexpr int SW = (D * 2 >= 128) ? 128 : D * 2;  // swizzle width (bytes) of the Q/K/V boxes
+  static constexpr int BOX_COLS = SW / 2;
+  static constexpr int NBOX = D / BOX_COLS;
+  static constexpr int BOX_BYTES = 128 * SW;
+  static constexpr int TILE_BYTES = 128 * D * 2;
+  static constexpr int P_BYTES = 128 * 128 * 2;
+  static constexpr int STAGES = 2;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + STAGES * TILE_BYTES;
+  static constexpr int OFF_P = OFF_V + STAGES * TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int TMEM_S = 0;      // S buffers: columns [0,128) and [128,256)
+  static constexpr int TMEM_O = 256;    // O accumulator: columns [256, 256 + D)
+};
+
+struct FwdBars {
+  uint64_t q_full;
+  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
+  uint64_t s_full[2], p_full[2], p_empty[2];
+  uint64_t o_full;
+  uint32_t tmem_base;
+};
+
+template <int D, bool BF16>
+__global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_constant__ FwdParams p) {
+  using Cfg = FwdCfg<D>;
+  constexpr int SW = Cfg::SW;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int m0 = (int)(gridDim.x - 1 - blockIdx.x) * 128;
+  const long long row0 = load_index(p.seq_offsets, p.offsets_i64, b);
+  int len = (int)(load_index(p.seq_offsets, p.offsets_i64, b + 1) - row0);
+  len = len < p.max_seq_len ? len : p.max_seq_len;
+  if (m0 >= len) return;
+  const int n_tgt = p.num_targets ? (int)load_index(p.num_targets, p.targets_i64, b) : -1;
+  const SeqMask msk = make_seq_mask(len, n_tgt, p.win, p.min_full, p.ctx);
+  const int mrows = min(128, len - m0);
+  int lo, hi;
+  kv_range_for_q_rows(msk, m0, m0 + mrows, &lo, &hi);
+  const int t0 = lo / 128;
+  const int T = (hi + 127) / 128 - t0;  // >= 1 (the diagonal tile)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + Cfg::OFF_Q;
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sP = smem + Cfg::OFF_P;
+  FwdBars* bars = reinterpret_cast<FwdBars*>(smem + Cfg::OFF_BAR);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bars->q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->k_full[i], 1);
+      mbar_init(&bars->k_empty[i], 1);
+      mbar_init(&bars->v_full[i], 1);
+      mbar_init(&bars->v_empty[i], 1);
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->p_full[i], 128);
+      mbar_init(&bars->p_empty[i], 1);
+    }
+    mbar_init(&bars->o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: Q, then K tiles ----------------
+      prefetch_tensormap(&p.tmQ);
+      prefetch_tensormap(&p.tmK);
+      mbar_arrive_expect_tx(&bars->q_full, Cfg::TILE_BYTES);
+#pragma unroll
+      for (int bx = 0; bx < Cfg::NBOX; ++bx)
+        tma_load_3d(sQ + bx * Cfg::BOX_BYTES, &p.tmQ, &bars->q_full, bx * Cfg::BOX_COLS, h, (int)(row0 + m0));
+      for (int i = 0; i < T; ++i) {
+        const int st = i & 1;
+        if (i >= 2) mbar_wait(&bars->k_empty[st], ((i >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&bars->k_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int bx = 0; bx < Cfg::NBOX; ++bx)
+          tma_load_3d(sK + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, &p.tmK, &bars->k_full[st], bx * Cfg::BOX_COLS, h,
+                      (int)(row0 + (long long)(t0 + i) * 128));
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ---------------- TMA producer: V tiles ----------------
+      prefetch_tensormap(&p.tmV);
+      for (int i = 0; i < T; ++i) {
+        const int st = i & 1;
+        if (i >= 2) mbar_wait(&bars->v_empty[st], ((i >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&bars->v_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int bx = 0; bx < Cfg::NBOX; ++bx)
+          tma_load_3d(sV + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, &p.tmV, &bars->v_full[st], bx * Cfg::BOX_COLS, h,
+                      (int)(row0 + (long long)(t0 + i) * 128));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc_qk = make_idesc(128, 128, false, false, BF16, BF16);
+      constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, BF16, BF16);
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+      auto issue_qk = [&](int i) {
+        const int st = i & 1;
+        mbar_wait(&bars->k_full[st], (i >> 1) & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
+          const uint64_t ad = desc_kmajor<SW>(q_addr + bx * Cfg::BOX_BYTES, off);
+          const uint64_t bd = desc_kmajor<SW>(k_addr + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, off);
+          mma_ss(tmem + Cfg::TMEM_S + st * 128, ad, bd, idesc_qk, ks > 0);
+        }
+        mma_commit(&bars->k_empty[st]);
+        mma_commit(&bars->s_full[st]);
+      };
+      mbar_wait(&bars->q_full, 0);
+      issue_qk(0);
+      if (T > 1) issue_qk(1);
+      for (int i = 0; i < T; ++i) {
+        const int st = i & 1;
+        mbar_wait(&bars->p_full[st], (i >> 1) & 1);
+        mbar_wait(&bars->v_full[st], (i >> 1) & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = desc_kmajor<128>(p_addr + st * Cfg::P_BYTES + (ks >> 2) * 16384, (ks & 3) * 32);
+          const uint64_t bd = desc_mnmajor<SW>(v_addr + st * Cfg::TILE_BYTES, ks * 16, Cfg::BOX_BYTES);
+          mma_ss(tmem + Cfg::TMEM_O, ad, bd, idesc_pv, (i > 0) || (ks > 0));
+        }
+        mma_commit(&bars->v_empty[st]);
+        mma_commit(&bars->p_empty[st]);
+        if (i + 2 < T) issue_qk(i + 2);
+      }
+      mma_commit(&bars->o_full);
+    }
+  } else if (warp >= 4) {
+    // ---------------- silu warpgroups ----------------
+    const int wg = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;              // query row inside the tile == TMEM lane
+    const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
+    const int i_pos = m0 + row;
+    const float ah = p.alpha_half;
+    const int full_lim = msk.fast ? min(m0, msk.has_tgt ? msk.max_id : 0x7fffffff) : -1;
+    uint8_t* sPw = sP + wg * Cfg::P_BYTES;
+    for (int i = wg, it = 0; i < T; i += 2, ++it) {
+      mbar_wait(&bars->s_full[wg], it & 1);
+      tc_fence_after_sync();
+      if (it >= 1) mbar_wait(&bars->p_empty[wg], (it - 1) & 1);
+      const int n0 = (t0 + i) * 128;
+      const bool full = (n0 + 128 <= full_lim);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tmem_ld32(tmem + Cfg::TMEM_S + wg * 128 + c * 32 + lane_bits, s);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float h0 = __uint_as_float(s[e]) * ah, h1 = __uint_as_float(s[e + 1]) * ah;
+          float p0 = fmaf(h0, tanh_approx(h0), h0);
+          float p1 = fmaf(h1, tanh_approx(h1), h1);
+          if (!full) {
+            const int j = n0 + c * 32 + e;
+            p0 = (j < len && mask_valid(msk, i_pos, j)) ? p0 : 0.f;
+            p1 = (j + 1 < len && mask_valid(msk, i_pos, j + 1)) ? p1 : 0.f;
+          }
+          pk[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const int cc = c * 4 + j4;  // 16-byte chunk index along the key dimension (0..15)
+          uint4 v = make_uint4(pk[4 * j4], pk[4 * j4 + 1], pk[4 * j4 + 2], pk[4 * j4 + 3]);
+          *reinterpret_cast<uint4*>(sPw + (cc >> 3) * 16384 + swizzled_chunk_offset<128>(row, cc & 7)) = v;
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->p_full[wg]);
+    }
+    // ---------------- epilogue: O (TMEM) -> * 1/N -> global ----------------
+    mbar_wait(&bars->o_full, 0);
+    tc_fence_after_sync();
+    constexpr int HALF = D / 2;
+    const int cbase = wg * HALF;
+    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + (row0 + m0 + row) * p.o_row_stride + (long long)h * p.o_head_stride + cbase;
+#pragma unroll
+    for (int c = 0; c < HALF / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld16(tmem + Cfg::TMEM_O + cbase + c * 16 + lane_bits, o);
+      tmem_ld_wait();
+      if (row < mrows) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          const float a = __uint_as_float(o[e]) * p.inv_n, bb = __uint_as_float(o[e + 1]) * p.inv_n;
+          pk[e >> 1] = BF16 ? pack_bf16x2(a, bb) : pack_f16x2(a, bb);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(orow + c * 16);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+static bool is_sm100() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    cached = (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.major == 10) ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+static bool aligned_view(const void* ptr, long long row_stride, long long head_stride) {
+  return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (row_stride % 8) == 0 && (head_stride % 8) == 0;
+}
+
+bool umma_fwd_supported(const hstu_attn_params& p) {
+  if (p.dtype != HSTU_BF16 && p.dtype != HSTU_F16) return false;
+  if (p.dqk != p.dv || (p.dqk != 32 && p.dqk != 64 && p.dqk != 128)) return false;
+  if (p.delta_q_len != 0 || p.pos_w != nullptr || p.ts_w != nullptr) return false;
+  if (p.total_rows >= (1ll << 31) - 256) return false;
+  if (!aligned_view(p.q, p.q_row_stride, p.q_head_stride) || !aligned_view(p.k, p.k_row_stride, p.k_head_stride) ||
+      !aligned_view(p.v, p.v_row_stride, p.v_head_stride) || !aligned_view(p.out, p.o_row_stride, p.o_head_stride))
+    return false;
+  return is_sm100();
+}
+
+template <int D, bool BF16>
+static int launch_fwd_umma(const hstu_attn_params& p, cudaStream_t st) {
+  using Cfg = FwdCfg<D>;
+  FwdParams fp;
+  memset(&fp, 0, sizeof(fp));
+  if (int e = make_tmap_rows_heads(&fp.tmQ, p.q, p.total_rows, p.heads, D, p.q_row_stride, p.q_head_stride, Cfg::BOX_COLS, 128)) return e;
+  if (int e = make_tmap_rows_heads(&fp.tmK, p.k, p.total_rows, p.heads, D, p.k_row_stride, p.k_head_stride, Cfg::BOX_COLS, 128)) return e;
+  if (int e = make_tmap_rows_heads(&fp.tmV, p.v, p.total_rows, p.heads, D, p.v_row_stride, p.v_head_stride, Cfg::BOX_COLS, 128)) return e;
+  fp.seq_offsets = p.seq_offsets;
+  fp.num_targets = p.num_targets;
+  fp.out = p.out;
+  fp.o_row_stride = p.o_row_stride;
+  fp.o_head_stride = p.o_head_stride;
+  fp.offsets_i64 = p.offsets_are_i64;
+  fp.targets_i64 = p.num_targets_are_i64;
+  fp.max_seq_len = p.max_seq_len;
+  fp.win = p.max_attn_len;
+  fp.min_full = p.min_full_attn_seq_len;
+  fp.ctx = p.contextual_seq_len;
+  fp.alpha_half = 0.5f * p.alpha;
+  fp.inv_n = 1.0f / (float)p.max_seq_len;
+  auto kern = attn_fwd_umma_kernel<D, BF16>;
+  HSTU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  dim3 grid((p.max_seq_len + 127) / 128, p.heads, p.batch);
+  kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(fp);
+  HSTU_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int attn_umma_fwd(const hstu_attn_params& p, cudaStream_t st) {
+  const bool bf = p.dtype == HSTU_BF16;
+  switch (p.dqk) {
+    case 32: return bf ? launch_fwd_umma<32, true>(p, st) : launch_fwd_umma<32, false>(p, st);
+    case 64: return bf ? launch_fwd_umma<64, true>(p, st) : launch_fwd_umma<64, false>(p, st);
+    case 128: return bf ? launch_fwd_umma<128, true>(p, st) : launch_fwd_umma<128, false>(p, st);
+  }
+  set_error("tcgen05 forward: unsupported head dim %d", p.dqk);
+  return HSTU_ERR_UNSUPPORTED;
+}
+
+}  // namespace hstu

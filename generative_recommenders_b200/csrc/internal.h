@@ -1,0 +1,44 @@
+// Internal (non-ABI) declarations shared by the translation units of libhstu_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "../../include/hstu_b200.h"
+
+namespace hstu {
+void set_error(const char* fmt, ...);
+
+// attn_generic.cu
+int attn_generic_fwd(const hstu_attn_params& p, cudaStream_t st);
+int attn_generic_bwd(const hstu_attn_params& p, cudaStream_t st);
+
+// attn_umma_fwd.cu / attn_umma_bwd.cu / umma_selftest.cu
+bool umma_supported(const hstu_attn_params& p, bool bwd);
+size_t umma_workspace_bytes(const hstu_attn_params& p, bool bwd);
+int attn_umma_fwd(const hstu_attn_params& p, cudaStream_t st);
+int attn_umma_bwd(const hstu_attn_params& p, cudaStream_t st);
+int umma_selftest(char* report, size_t report_bytes);
+
+// norm.cu
+int layer_norm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, long long n, int D,
+                   long long xs, long long ys, float eps, int dtype, int swish, bool rms, cudaStream_t st);
+int layer_norm_bwd(const void* dy, const void* x, const void* w, const void* b, const float* mean, const float* rstd,
+                   void* dx, float* dw, float* db, float* partial, long long n, int D, long long xs, long long dys,
+                   long long dxs, int dtype, int swish, bool rms, cudaStream_t st);
+int norm_mul_dropout_fwd(const void* attn, const void* u, const void* w, const void* b, void* out, float* mean,
+                         float* rstd, long long n, int H, int dv, long long as, long long us, float eps, float p,
+                         unsigned long long seed, int dtype, int silu_u, int concat, int gn, cudaStream_t st);
+int norm_mul_dropout_bwd(const void* dout, const void* attn, const void* u, const void* w, const void* b,
+                         const float* mean, const float* rstd, void* dattn, void* du, float* dw, float* db,
+                         float* partial, long long n, int H, int dv, long long as, long long us, long long das,
+                         long long dus, float p, unsigned long long seed, int dtype, int silu_u, int concat, int gn,
+                         cudaStream_t st);
+int silu_fwd_bwd(const void* x, const void* dy, void* out, long long n, int cols, long long xs, long long dys,
+                 long long os, int dtype, bool bwd, cudaStream_t st);
+int norm_partial_rows();
+
+// jagged.cu
+int jagged_concat_split(bool split, const void* a, const void* b, void* c, void* c2, const void* off_l, const void* off_r,
+                        int is_i64, int batch, int dense_l, int dense_r, int n_prefix, int D, int elem_bytes,
+                        int max_seq_len, cudaStream_t st);
+}  // namespace hstu

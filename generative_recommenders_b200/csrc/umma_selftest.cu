@@ -1,0 +1,344 @@
+// On-device self test of the tcgen05 / TMA building blocks (exported as hstu_umma_selftest).
+//
+// One small GEMM kernel  D[128, N] = A[128, K] * B[N, K]^T  exercises, with exactly-representable integer data,
+// every operand layout the attention kernels rely on:
+//   * K-major operands loaded by TMA with 128B / 64B / 32B swizzle (Q, K, dO tiles),
+//   * MN-major operands loaded by TMA (V for P.V; Q, dO, K for the backward GEMMs),
+//   * A written by the threads themselves into the swizzled layout (P / dS tiles),
+//   * A read from TMEM (tcgen05.mma with a TMEM A operand, written by tcgen05.st),
+//   * accumulator read-back with tcgen05.ld 32x32b.
+// A second micro-benchmark measures SFU (MUFU) throughput of the candidate sigmoid formulations.
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "internal.h"
+#include "umma.cuh"
+
+namespace hstu {
+using namespace umma;
+
+struct StCfg {
+  int N, K;
+  int a_mode;  // 0 K-major TMA, 1 MN-major TMA, 2 K-major written by threads, 3 TMEM
+  int b_mode;  // 0 K-major TMA, 1 MN-major TMA
+  int sw_a, sw_b;
+  int variant;  // 1: swap LBO/SBO of MN-major descriptors (diagnostic)
+};
+
+template <int SW>
+__device__ uint64_t op_desc(int mode, uint32_t base, int rows_k_or_mn, int k_step, int variant) {
+  // mode 0/2: K-major tile of `rows` rows; boxes along K each rows*SW bytes
+  if (mode == 0 || mode == 2) {
+    const uint32_t kbyte = k_step * 32;
+    const uint32_t box = kbyte / SW, off = kbyte % SW;
+    return desc_kmajor<SW>(base + box * rows_k_or_mn * SW, off);
+  }
+  // mode 1: MN-major tile: boxes along MN, each Krows*SW bytes; rows_k_or_mn = K rows of the tile
+  uint64_t d = desc_mnmajor<SW>(base, k_step * 16, rows_k_or_mn * SW);
+  if (variant == 1) d = make_smem_desc(base + k_step * 16 * SW, 8 * SW, rows_k_or_mn * SW, swizzle_layout_type(SW));
+  return d;
+}
+
+__device__ uint64_t op_desc_rt(int sw, int mode, uint32_t base, int rows, int k_step, int variant) {
+  if (sw == 128) return op_desc<128>(mode, base, rows, k_step, variant);
+  if (sw == 64) return op_desc<64>(mode, base, rows, k_step, variant);
+  return op_desc<32>(mode, base, rows, k_step, variant);
+}
+
+__device__ uint32_t swz_off_rt(int sw, uint32_t row, uint32_t chunk) {
+  if (sw == 128) return swizzled_chunk_offset<128>(row, chunk);
+  if (sw == 64) return swizzled_chunk_offset<64>(row, chunk);
+  return swizzled_chunk_offset<32>(row, chunk);
+}
+
+__global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                            const __grid_constant__ CUtensorMap tmB,
+                                                            const __nv_bfloat16* __restrict__ Ag, float* __restrict__ Dg,
+                                                            StCfg cfg, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_full, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int M = 128, N = cfg.N, K = cfg.K;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * 128 * 2 * 2;  // A tile is at most 128 x 256 bf16... (we cap K at 128 for A) -> 64 KB reserved
+  if (tid == 0) {
+    mbar_init(&bar_full, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_d = tmem_base;          // accumulator: columns [0, N)
+  const uint32_t tmem_a = tmem_base + 256;    // TMEM A operand: columns [256, 256 + K/2)
+
+  if (tid == 0) {
+    uint32_t bytes = 0;
+    // A
+    if (cfg.a_mode == 0) {
+      const int cols = cfg.sw_a / 2, nbox = K / cols;
+      for (int b = 0; b < nbox; ++b) tma_load_3d(sA + b * M * cfg.sw_a, &tmA, &bar_full, b * cols, 0, 0);
+      bytes += M * K * 2;
+    } else if (cfg.a_mode == 1) {
+      const int cols = cfg.sw_a / 2, nbox = M / cols;
+      for (int b = 0; b < nbox; ++b) tma_load_3d(sA + b * K * cfg.sw_a, &tmA, &bar_full, b * cols, 0, 0);
+      bytes += M * K * 2;
+    }
+    // B
+    if (cfg.b_mode == 0) {
+      const int cols = cfg.sw_b / 2, nbox = K / cols;
+      for (int b = 0; b < nbox; ++b) tma_load_3d(sB + b * N * cfg.sw_b, &tmB, &bar_full, b * cols, 0, 0);
+    } else {
+      const int cols = cfg.sw_b / 2, nbox = N / cols;
+      for (int b = 0; b < nbox; ++b) tma_load_3d(sB + b * K * cfg.sw_b, &tmB, &bar_full, b * cols, 0, 0);
+    }
+    bytes += N * K * 2;
+    mbar_arrive_expect_tx(&bar_full, bytes);
+  }
+  if (cfg.a_mode == 2) {
+    // thread = row; write A[row][:] (K-major) into the swizzled boxes by hand, 16 bytes at a time
+    const int chunks_per_box = cfg.sw_a / 16;
+    for (int c = 0; c < K / 8; ++c) {
+      uint4 v = *reinterpret_cast<const uint4*>(Ag + (size_t)tid * K + c * 8);
+      const int box = c / chunks_per_box, cc = c % chunks_per_box;
+      *reinterpret_cast<uint4*>(sA + box * M * cfg.sw_a + swz_off_rt(cfg.sw_a, tid, cc)) = v;
+    }
+    fence_proxy_async_smem();
+  } else if (cfg.a_mode == 3) {
+    // thread = row = TMEM lane; 16 bf16 (one UMMA K step) occupy 8 TMEM columns
+    for (int c = 0; c < K / 32; ++c) {
+      uint32_t r[16];
+      const uint4* src = reinterpret_cast<const uint4*>(Ag + (size_t)tid * K + c * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 v = src[i];
+        r[4 * i + 0] = v.x;
+        r[4 * i + 1] = v.y;
+        r[4 * i + 2] = v.z;
+        r[4 * i + 3] = v.w;
+      }
+      tmem_st16(tmem_a + ((uint32_t)(warp * 32) << 16) + c * 16, r);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    mbar_wait(&bar_full, 0);
+    tc_fence_after_sync();
+    const uint32_t idesc = make_idesc(M, N, cfg.a_mode == 1, cfg.b_mode == 1, true, true);
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+    for (int k = 0; k < K / 16; ++k) {
+      const uint64_t bd = op_desc_rt(cfg.sw_b, cfg.b_mode, b_base, cfg.b_mode == 1 ? K : N, k, cfg.variant);
+      if (cfg.a_mode == 3) {
+        mma_ts(tmem_d, tmem_a + k * 8, bd, idesc, k > 0);
+      } else {
+        const uint64_t ad = op_desc_rt(cfg.sw_a, cfg.a_mode, a_base, cfg.a_mode == 1 ? K : M, k, cfg.variant);
+        mma_ss(tmem_d, ad, bd, idesc, k > 0);
+      }
+    }
+    mma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after_sync();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Dg[(size_t)tid * N + c0 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (tid == 0) *status = 1;
+}
+
+// ---- MUFU micro-benchmark ------------------------------------------------------------------------
+template <int MODE>
+__global__ void mufu_bench_kernel(float* out, int iters) {
+  float a = threadIdx.x * 1e-3f, b = a + 0.5f, c = a + 1.0f, d = a + 1.5f;
+  uint32_t pa = 0x3c003800u + threadIdx.x, pb = 0x38003c00u + threadIdx.x;
+  for (int i = 0; i < iters; ++i) {
+    if (MODE == 0) {  // tanh.approx.f32
+      a = tanh_approx(a); b = tanh_approx(b); c = tanh_approx(c); d = tanh_approx(d);
+    } else if (MODE == 1) {  // ex2 + rcp
+      asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(a)); asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(a));
+      asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(b)); asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(b));
+    } else if (MODE == 2) {  // tanh.approx.bf16x2
+      asm("tanh.approx.bf16x2 %0, %0;" : "+r"(pa)); asm("tanh.approx.bf16x2 %0, %0;" : "+r"(pb));
+    } else if (MODE == 3) {  // tanh.approx.f16x2
+      asm("tanh.approx.f16x2 %0, %0;" : "+r"(pa)); asm("tanh.approx.f16x2 %0, %0;" : "+r"(pb));
+    } else if (MODE == 4) {  // ex2.approx.f16x2
+      asm("ex2.approx.f16x2 %0, %0;" : "+r"(pa)); asm("ex2.approx.f16x2 %0, %0;" : "+r"(pb));
+    } else if (MODE == 5) {  // FMA pipe reference: 4 independent FFMA chains
+      a = fmaf(a, 1.0001f, 0.5f); b = fmaf(b, 1.0001f, 0.5f); c = fmaf(c, 1.0001f, 0.5f); d = fmaf(d, 1.0001f, 0.5f);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a + b + c + d + __uint_as_float(pa) + __uint_as_float(pb);
+}
+
+static void rep(char* buf, size_t cap, const char* fmt, ...) {
+  size_t n = strlen(buf);
+  if (n + 1 >= cap) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf + n, cap - n, fmt, ap);
+  va_end(ap);
+}
+
+static int run_gemm_case(const char* name, StCfg cfg, char* report, size_t cap) {
+  const int M = 128, N = cfg.N, K = cfg.K;
+  std::vector<__nv_bfloat16> hA((size_t)M * K), hB((size_t)N * K);   // logical A[m][k], B[n][k]
+  std::vector<float> ref((size_t)M * N, 0.f), got((size_t)M * N, 0.f);
+  uint32_t s = 12345u + (uint32_t)(N * 131 + K * 7 + cfg.a_mode * 3 + cfg.b_mode);
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (float)((int)((s >> 16) % 7) - 3); };
+  for (auto& x : hA) x = __float2bfloat16(rnd());
+  for (auto& x : hB) x = __float2bfloat16(rnd());
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) acc += __bfloat162float(hA[(size_t)m * K + k]) * __bfloat162float(hB[(size_t)n * K + k]);
+      ref[(size_t)m * N + n] = acc;
+    }
+  // device storage: K-major operands as [rows][K]; MN-major operands as [K][rows]
+  std::vector<__nv_bfloat16> dAh = hA, dBh = hB;
+  if (cfg.a_mode == 1) for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) dAh[(size_t)k * M + m] = hA[(size_t)m * K + k];
+  if (cfg.b_mode == 1) for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) dBh[(size_t)k * N + n] = hB[(size_t)n * K + k];
+  __nv_bfloat16 *dA = nullptr, *dB = nullptr;
+  float* dD = nullptr;
+  int* dS = nullptr;
+  cudaMalloc(&dA, dAh.size() * 2);
+  cudaMalloc(&dB, dBh.size() * 2);
+  cudaMalloc(&dD, got.size() * 4);
+  cudaMalloc(&dS, 4);
+  cudaMemcpy(dA, dAh.data(), dAh.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, dBh.data(), dBh.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemset(dD, 0, got.size() * 4);
+  cudaMemset(dS, 0, 4);
+  CUtensorMap tA, tB;
+  int rc = 0;
+  if (cfg.a_mode == 1) rc |= make_tmap_rows_heads(&tA, dA, K, 1, M, M, M, cfg.sw_a / 2, K);
+  else rc |= make_tmap_rows_heads(&tA, dA, M, 1, K, K, K, cfg.sw_a / 2, M);
+  if (cfg.b_mode == 1) rc |= make_tmap_rows_heads(&tB, dB, K, 1, N, N, N, cfg.sw_b / 2, K);
+  else rc |= make_tmap_rows_heads(&tB, dB, N, 1, K, K, K, cfg.sw_b / 2, N);
+  int fails = 0;
+  if (rc != 0) {
+    rep(report, cap, "%-34s TENSORMAP-ERROR %s\n", name, hstu_last_error());
+    fails = 1;
+  } else {
+    const size_t smem = 1024 + 65536 + 65536;
+    cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    umma_selftest_kernel<<<1, 128, smem>>>(tA, tB, dA, dD, cfg, dS);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      rep(report, cap, "%-34s CUDA-ERROR %s\n", name, cudaGetErrorString(e));
+      return -1000;  // context is probably poisoned
+    }
+    cudaMemcpy(got.data(), dD, got.size() * 4, cudaMemcpyDeviceToHost);
+    size_t bad = 0;
+    double maxerr = 0;
+    for (size_t i = 0; i < got.size(); ++i) {
+      double er = fabs((double)got[i] - (double)ref[i]);
+      if (er > maxerr) maxerr = er;
+      if (er != 0.0) ++bad;
+    }
+    rep(report, cap, "%-34s %s  mismatches=%zu/%zu maxerr=%g  (d[0]=%g ref=%g, d[last]=%g ref=%g)\n", name,
+        bad == 0 ? "PASS" : "FAIL", bad, got.size(), maxerr, got[0], ref[0], got.back(), ref.back());
+    fails = bad == 0 ? 0 : 1;
+  }
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dD);
+  cudaFree(dS);
+  return fails;
+}
+
+template <int MODE>
+static void mufu_case(const char* name, int per_iter, char* report, size_t cap) {
+  float* out = nullptr;
+  const int blocks = 148 * 8, threads = 256, iters = 4096;
+  cudaMalloc(&out, sizeof(float) * blocks * threads);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  mufu_bench_kernel<MODE><<<blocks, threads>>>(out, 64);
+  cudaEventRecord(e0);
+  mufu_bench_kernel<MODE><<<blocks, threads>>>(out, iters);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double ops = (double)blocks * threads * iters * per_iter;
+  rep(report, cap, "mufu/%-28s %8.1f G results/s (%.3f ms)\n", name, ops / (ms * 1e-3) / 1e9, ms);
+  cudaFree(out);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
+int umma_selftest(char* report, size_t cap) {
+  if (report == nullptr || cap < 64) return -1;
+  report[0] = 0;
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    rep(report, cap, "no CUDA device\n");
+    return -1;
+  }
+  rep(report, cap, "device: %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+  if (prop.major != 10) {
+    rep(report, cap, "not an sm_100 device: tcgen05 self test skipped\n");
+    return -1;
+  }
+  struct Case { const char* name; StCfg cfg; };
+  const Case cases[] = {
+      //                                   N    K   a  b  swa  swb var
+      {"KK sw128 K64 N128",               {128, 64, 0, 0, 128, 128, 0}},
+      {"KK sw128 K128 N128 (2 boxes)",    {128, 128, 0, 0, 128, 128, 0}},
+      {"KK sw64 K32 N128",                {128, 32, 0, 0, 64, 64, 0}},
+      {"KK sw32 K16 N64",                 {64, 16, 0, 0, 32, 32, 0}},
+      {"KK sw128 K128 N256",              {256, 128, 0, 0, 128, 128, 0}},
+      {"B MN sw128 N128 K128",            {128, 128, 0, 1, 128, 128, 0}},
+      {"B MN sw128 N64 K128",             {64, 128, 0, 1, 128, 128, 0}},
+      {"B MN sw64 N32 K128",              {32, 128, 0, 1, 128, 64, 0}},
+      {"B MN sw128 N256 K64",             {256, 64, 0, 1, 128, 128, 0}},
+      {"B MN sw128 N128 K128 [swapped]",  {128, 128, 0, 1, 128, 128, 1}},
+      {"A MN sw128, B K sw128 K128 N128", {128, 128, 1, 0, 128, 128, 0}},
+      {"A MN sw128, B K sw64 K128 N32",   {32, 128, 1, 0, 128, 64, 0}},
+      {"A MN sw128, B MN sw64 N32",       {32, 128, 1, 1, 128, 64, 0}},
+      {"A MN sw128, B MN sw128 N64",      {64, 128, 1, 1, 128, 128, 0}},
+      {"A MN sw128, B MN sw128 N128",     {128, 128, 1, 1, 128, 128, 0}},
+      {"A manual sw128 K128, B MN sw64",  {32, 128, 2, 1, 128, 64, 0}},
+      {"A manual sw128 K128, B MN sw128", {128, 128, 2, 1, 128, 128, 0}},
+      {"A manual sw64 K32, B K sw64",     {128, 32, 2, 0, 64, 64, 0}},
+      {"A TMEM K128, B MN sw64 N32",      {32, 128, 3, 1, 128, 64, 0}},
+      {"A TMEM K128, B MN sw128 N128",    {128, 128, 3, 1, 128, 128, 0}},
+      {"A TMEM K64, B K sw128 N128",      {128, 64, 3, 0, 128, 128, 0}},
+  };
+  int fails = 0;
+  for (const Case& c : cases) {
+    int r = run_gemm_case(c.name, c.cfg, report, cap);
+    if (r == -1000) {
+      rep(report, cap, "aborting self test after a CUDA error\n");
+      return fails + 100;
+    }
+    if (c.cfg.variant == 0) fails += r;  // diagnostic variants do not count
+  }
+  mufu_case<0>("tanh.approx.f32", 4, report, cap);
+  mufu_case<1>("ex2+rcp f32 (sigmoid)", 2, report, cap);
+  mufu_case<2>("tanh.approx.bf16x2", 4, report, cap);
+  mufu_case<3>("tanh.approx.f16x2", 4, report, cap);
+  mufu_case<4>("ex2.approx.f16x2", 4, report, cap);
+  mufu_case<5>("ffma f32 (reference)", 4, report, cap);
+  rep(report, cap, "failed checks: %d\n", fails);
+  return fails;
+}
+
+}  // namespace hstu

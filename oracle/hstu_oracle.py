@@ -110,13 +110,15 @@ def hstu_mha_fwd(
                 n, None if nt is None else int(nt[b]), max_attn_len, contextual_seq_len, min_full_attn_seq_len
             )
         )
-        qb = q[s : s + n].to(dtype).transpose(0, 1)  # [H, n, d]
-        kb = k[s : s + n].to(dtype).transpose(0, 1)
-        vb = v[s : s + n].to(dtype).transpose(0, 1)
-        sc = torch.matmul(qb, kb.transpose(1, 2)) * alpha  # :150
-        p = torch.nn.functional.silu(sc) / max_seq_len  # :151
-        p = p * m.to(dtype)  # :163
-        out[s : s + n] = torch.matmul(p, vb).transpose(0, 1)  # :166
+        hc = max(1, min(H, (1 << 26) // max(1, n * n)))  # heads per chunk: bounds the [hc, n, n] temporaries
+        for h0 in range(0, H, hc):
+            qb = q[s : s + n, h0 : h0 + hc].to(dtype).transpose(0, 1)  # [hc, n, d]
+            kb = k[s : s + n, h0 : h0 + hc].to(dtype).transpose(0, 1)
+            vb = v[s : s + n, h0 : h0 + hc].to(dtype).transpose(0, 1)
+            sc = torch.matmul(qb, kb.transpose(1, 2)) * alpha  # :150
+            p = torch.nn.functional.silu(sc) / max_seq_len  # :151
+            p = p * m.to(dtype)  # :163
+            out[s : s + n, h0 : h0 + hc] = torch.matmul(p, vb).transpose(0, 1)  # :166
     return out
 
 
@@ -157,18 +159,21 @@ def hstu_mha_bwd(
                 n, None if nt is None else int(nt[b]), max_attn_len, contextual_seq_len, min_full_attn_seq_len
             )
         ).to(dtype)
-        qb = q[s : s + n].to(dtype).transpose(0, 1)
-        kb = k[s : s + n].to(dtype).transpose(0, 1)
-        vb = v[s : s + n].to(dtype).transpose(0, 1)
-        dob = dout[s : s + n].to(dtype).transpose(0, 1)
-        S = torch.matmul(qb, kb.transpose(1, 2)) * alpha
-        sig = torch.sigmoid(S)
-        P = c * S * sig * m
-        dv_[s : s + n] = torch.matmul(P.transpose(1, 2), dob).transpose(0, 1)
-        dP = torch.matmul(dob, vb.transpose(1, 2))
-        dS = c * dP * sig * (1.0 + S * (1.0 - sig)) * m
-        dq[s : s + n] = (alpha * torch.matmul(dS, kb)).transpose(0, 1)
-        dk[s : s + n] = (alpha * torch.matmul(dS.transpose(1, 2), qb)).transpose(0, 1)
+        H = q.shape[1]
+        hc = max(1, min(H, (1 << 26) // max(1, n * n)))
+        for h0 in range(0, H, hc):
+            qb = q[s : s + n, h0 : h0 + hc].to(dtype).transpose(0, 1)
+            kb = k[s : s + n, h0 : h0 + hc].to(dtype).transpose(0, 1)
+            vb = v[s : s + n, h0 : h0 + hc].to(dtype).transpose(0, 1)
+            dob = dout[s : s + n, h0 : h0 + hc].to(dtype).transpose(0, 1)
+            S = torch.matmul(qb, kb.transpose(1, 2)) * alpha
+            sig = torch.sigmoid(S)
+            P = c * S * sig * m
+            dv_[s : s + n, h0 : h0 + hc] = torch.matmul(P.transpose(1, 2), dob).transpose(0, 1)
+            dP = torch.matmul(dob, vb.transpose(1, 2))
+            dS = c * dP * sig * (1.0 + S * (1.0 - sig)) * m
+            dq[s : s + n, h0 : h0 + hc] = (alpha * torch.matmul(dS, kb)).transpose(0, 1)
+            dk[s : s + n, h0 : h0 + hc] = (alpha * torch.matmul(dS.transpose(1, 2), qb)).transpose(0, 1)
     return dq, dk, dv_
 
 
@@ -455,6 +460,44 @@ def split_2D_jagged(values, max_len_left=None, max_len_right=None, offsets_left=
     left[torch.from_numpy(src[src >= 0])] = values[isl]
     right[torch.from_numpy(-src[src < 0] - 1)] = values[~isl]
     return left, right
+
+
+# --------------------------------------------------------------------------------------
+# autograd wrapper over the explicit forward / backward (used by the CPU-baseline timing: bounded memory)
+# --------------------------------------------------------------------------------------
+
+
+class OracleAttention(torch.autograd.Function):
+    """hstu_mha_fwd / hstu_mha_bwd under autograd, so that a whole layer can be differentiated on CPU without
+    autograd retaining the [H, n, n] temporaries of every op."""
+
+    @staticmethod
+    def forward(ctx, max_seq_len, alpha, q, k, v, seq_offsets, num_targets, max_attn_len, contextual_seq_len):
+        ctx.save_for_backward(q, k, v, seq_offsets, num_targets)
+        ctx.cfg = (max_seq_len, alpha, max_attn_len, contextual_seq_len)
+        return hstu_mha_fwd(max_seq_len, alpha, q, k, v, seq_offsets, num_targets, max_attn_len, contextual_seq_len)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, seq_offsets, num_targets = ctx.saved_tensors
+        n, alpha, mal, ctxlen = ctx.cfg
+        dq, dk, dv = hstu_mha_bwd(n, alpha, dout, q, k, v, seq_offsets, num_targets, mal, ctxlen)
+        return None, None, dq, dk, dv, None, None, None, None
+
+
+def stu_layer_fwd_bwd_timed(x, x_offsets, max_seq_len, num_targets, params, num_heads, attn_dim, hidden_dim):
+    """One STU layer forward + backward on CPU (fp32), attention through OracleAttention.  Returns (y, dx)."""
+    x = x.detach().float().requires_grad_()
+    ps = {k: v.detach().float().requires_grad_() for k, v in params.items()}
+    alpha = 1.0 / math.sqrt(attn_dim)
+    u, q, k, v = hstu_compute_uqvk_fwd(x, ps["_input_norm_weight"], ps["_input_norm_bias"], 1e-6, num_heads, attn_dim,
+                                       hidden_dim, ps["_uvqk_weight"], ps["_uvqk_beta"])
+    attn = OracleAttention.apply(max_seq_len, alpha, q, k, v, x_offsets, num_targets, 0, 0)
+    y = hstu_compute_output_fwd(attn.reshape(-1, num_heads * hidden_dim), u, x, ps["_output_norm_weight"],
+                                ps["_output_norm_bias"], ps["_output_weight"], 1e-6, False, True, False, num_heads,
+                                hidden_dim)
+    y.backward(torch.ones_like(y))
+    return y.detach(), x.grad
 
 
 # --------------------------------------------------------------------------------------
