@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--lmax", type=int, default=8192)
     ap.add_argument("--layers", type=int, default=16)
     ap.add_argument("--attn-dim", type=int, default=128, help="head dim of the attn microbench workload")
+    ap.add_argument("--attn-heads", type=int, default=4)
     ap.add_argument("--attn-impl", type=int, default=0, help="0 auto, 1 generic kernels, 2 force tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -229,7 +230,7 @@ def run_ours(args):
         per_step_calls = layers
     else:
         d = args.attn_dim
-        Ha = 4
+        Ha = args.attn_heads
         x = torch.empty(L, Ha, 3 * d, device=dev, dtype=torch.bfloat16).uniform_(-0.01, 0.01)
         q, k, v = torch.split(x, [d, d, d], dim=-1)
         q.requires_grad_(True), k.requires_grad_(True), v.requires_grad_(True)
@@ -254,7 +255,7 @@ def run_ours(args):
 
         units_per_step = args.batch
         d2h_bytes = 2
-        cfg = {"workload": f"hstu_mha fwd+bwd microbench (hstu_attention_bench.py recipe): B={args.batch}, H=4, d={d}, "
+        cfg = {"workload": f"hstu_mha fwd+bwd microbench (hstu_attention_bench.py recipe): B={args.batch}, H={Ha}, d={d}, "
                            f"Lmax={args.lmax}, bf16, alpha=1/d, targets<=20", "global_batch": args.batch * world,
                "seq_len": args.lmax, "rows_per_gpu": L, "parallelism": f"dp{world} (independent shards)",
                "l2": f"q,k,v,o,grads = {L * Ha * d * 2 * 11 / 1e6:.0f} MB per step > 126 MB L2" }

@@ -1,27 +1,460 @@
-// Jagged HSTU attention backward on tcgen05 -- dispatch glue (kernel: see below).
+// Jagged HSTU attention backward on tcgen05 + TMEM with TMA-staged tiles.  bf16 / fp16, dqk == dv in {32, 64}.
+//
+// One CTA per (128-row KEY tile, head, sequence); early key tiles (the heavy ones under a causal mask) are scheduled
+// first.  K and V of the tile stay in shared memory; the CTA streams the query tiles that can attend to it
+// (Q_i and dO_i, 2-stage TMA ring) and per query tile issues five tcgen05 GEMMs (accumulators in TMEM):
+//     S^T  = K Q_i^T          (A = K  K-major,  B = Q_i  K-major)      [kv x q]
+//     dP^T = V dO_i^T         (A = V  K-major,  B = dO_i K-major)      [kv x q]
+//   -- two warpgroups (one key row per thread, 64 query columns each) turn S^T, dP^T into
+//        P^T  = silu(alpha S)            * mask      (1/N folded into the dV epilogue)
+//        dS^T = dP sig (1 + x (1 - sig)) * mask      (alpha/N folded into the dK epilogue / dQ convert)
+//      as bf16 tiles in shared memory ([kv][q], q contiguous, 128B swizzle) --
+//     dV  += P^T  dO_i        (A = P^T  K-major,  B = dO_i MN-major)    [kv x d]   accumulates over all query tiles
+//     dK  += dS^T Q_i         (A = dS^T K-major,  B = Q_i  MN-major)    [kv x d]
+//     dQ_i = dS   K           (A = dS^T tile read MN-major, B = K MN-major)  [q x d]
+//   dQ_i is added to an fp32 accumulator in global memory with 128-bit vector reductions (each key-tile CTA
+//   contributes to every later query tile); a small convert kernel scales it by alpha/N and writes bf16 dq.
+//
+// Reference math: ops/triton/triton_hstu_attention.py:995-1006,1222 and SURVEY.md appendix A; unlike the Triton
+// kernel dQ is accumulated in fp32, not in the input dtype (triton_attention_utils.py:47-60).
 #include "common.cuh"
 #include "internal.h"
 #include "umma.cuh"
 
 namespace hstu {
+using namespace umma;
 
 bool umma_fwd_supported(const hstu_attn_params& p);
 
+struct alignas(64) BwdParams {
+  CUtensorMap tmQ, tmK, tmV, tmDO;
+  const void* seq_offsets;
+  const void* num_targets;
+  void* dk;
+  void* dv;
+  float* dq_acc;  // [L, H, D] fp32, zero-initialised
+  long long dk_row_stride, dk_head_stride, dv_row_stride, dv_head_stride;
+  int offsets_i64, targets_i64;
+  int max_seq_len, heads;
+  int win, min_full, ctx;
+  float alpha_half;
+  float dv_scale;  // 1 / N
+  float dk_scale;  // alpha / N
+};
+
+template <int D>
+struct BwdCfg {
+  static constexpr int SW = (D * 2 >= 128) ? 128 : D * 2;
+  static constexpr int BOX_COLS = SW / 2;
+  static constexpr int NBOX = D / BOX_COLS;
+  static constexpr int BOX_BYTES = 128 * SW;
+  static constexpr int TILE_BYTES = 128 * D * 2;
+  static constexpr int PT_BYTES = 128 * 128 * 2;
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + TILE_BYTES;
+  static constexpr int OFF_Q = OFF_V + TILE_BYTES;        // 2 stages
+  static constexpr int OFF_DO = OFF_Q + 2 * TILE_BYTES;   // 2 stages
+  static constexpr int OFF_PT = OFF_DO + 2 * TILE_BYTES;
+  static constexpr int OFF_DST = OFF_PT + PT_BYTES;
+  static constexpr int OFF_BAR = OFF_DST + PT_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int TMEM_ST = 0;          // S^T   [0,128)
+  static constexpr int TMEM_DPT = 128;       // dP^T  [128,256)
+  static constexpr int TMEM_DV = 256;        // dV    [256, 256+D)
+  static constexpr int TMEM_DK = 256 + D;    // dK
+  static constexpr int TMEM_DQ = 256 + 2 * D;  // dQ_i
+  static_assert(256 + 3 * D <= 512, "TMEM budget");
+};
+
+struct BwdBars {
+  uint64_t kv_full;
+  uint64_t q_full[2], q_empty[2];
+  uint64_t s_full, pds_full, pds_empty, dq_full, dq_empty, fin_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int D, bool BF16>
+__global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_constant__ BwdParams p) {
+  using Cfg = BwdCfg<D>;
+  constexpr int SW = Cfg::SW;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int n0 = (int)blockIdx.x * 128;
+  const long long row0 = load_index(p.seq_offsets, p.offsets_i64, b);
+  int len = (int)(load_index(p.seq_offsets, p.offsets_i64, b + 1) - row0);
+  len = len < p.max_seq_len ? len : p.max_seq_len;
+  if (n0 >= len) return;
+  const int n_tgt = p.num_targets ? (int)load_index(p.num_targets, p.targets_i64, b) : -1;
+  const SeqMask msk = make_seq_mask(len, n_tgt, p.win, p.min_full, p.ctx);
+  const int nrows = min(128, len - n0);
+  int lo, hi, ctx_hi;
+  q_range_for_kv_rows(msk, n0, n0 + nrows, &lo, &hi, &ctx_hi);
+  // query tiles: the contextual prefix tiles that lie strictly before the main range, then the main range
+  const int main_t0 = lo / 128;
+  const int n_main = (hi + 127) / 128 - main_t0;
+  const int n_pre = min((ctx_hi + 127) / 128, main_t0);
+  const int T = n_pre + n_main;
+  auto q_tile = [&](int i) { return i < n_pre ? i : main_t0 + (i - n_pre); };
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sQ = smem + Cfg::OFF_Q;
+  uint8_t* sDO = smem + Cfg::OFF_DO;
+  uint8_t* sPT = smem + Cfg::OFF_PT;
+  uint8_t* sDST = smem + Cfg::OFF_DST;
+  BwdBars* bars = reinterpret_cast<BwdBars*>(smem + Cfg::OFF_BAR);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bars->kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->q_full[i], 1);
+      mbar_init(&bars->q_empty[i], 1);
+    }
+    mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->pds_full, 256);
+    mbar_init(&bars->pds_empty, 1);
+    mbar_init(&bars->dq_full, 1);
+    mbar_init(&bars->dq_empty, 256);
+    mbar_init(&bars->fin_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      prefetch_tensormap(&p.tmK);
+      prefetch_tensormap(&p.tmV);
+      prefetch_tensormap(&p.tmQ);
+      prefetch_tensormap(&p.tmDO);
+      mbar_arrive_expect_tx(&bars->kv_full, 2 * Cfg::TILE_BYTES);
+#pragma unroll
+      for (int bx = 0; bx < Cfg::NBOX; ++bx) {
+        tma_load_3d(sK + bx * Cfg::BOX_BYTES, &p.tmK, &bars->kv_full, bx * Cfg::BOX_COLS, h, (int)(row0 + n0));
+        tma_load_3d(sV + bx * Cfg::BOX_BYTES, &p.tmV, &bars->kv_full, bx * Cfg::BOX_COLS, h, (int)(row0 + n0));
+      }
+      for (int i = 0; i < T; ++i) {
+        const int st = i & 1;
+        if (i >= 2) mbar_wait(&bars->q_empty[st], ((i >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&bars->q_full[st], 2 * Cfg::TILE_BYTES);
+        const int qrow = (int)(row0 + (long long)q_tile(i) * 128);
+#pragma unroll
+        for (int bx = 0; bx < Cfg::NBOX; ++bx) {
+          tma_load_3d(sQ + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, &p.tmQ, &bars->q_full[st], bx * Cfg::BOX_COLS, h, qrow);
+          tma_load_3d(sDO + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, &p.tmDO, &bars->q_full[st], bx * Cfg::BOX_COLS, h, qrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc_s = make_idesc(128, 128, false, false, BF16, BF16);   // S^T, dP^T
+      constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dV, dK: A K-major, B MN-major
+      constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // dQ: A MN-major, B MN-major
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
+      const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
+      auto issue_s = [&](int i) {
+        const int st = i & 1;
+        mbar_wait(&bars->q_full[st], (i >> 1) & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
+          mma_ss(tmem + Cfg::TMEM_ST, desc_kmajor<SW>(k_addr + bx * Cfg::BOX_BYTES, off),
+                 desc_kmajor<SW>(q_addr + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, off), idesc_s, ks > 0);
+        }
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
+          mma_ss(tmem + Cfg::TMEM_DPT, desc_kmajor<SW>(v_addr + bx * Cfg::BOX_BYTES, off),
+                 desc_kmajor<SW>(do_addr + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, off), idesc_s, ks > 0);
+        }
+        mma_commit(&bars->s_full);
+      };
+      mbar_wait(&bars->kv_full, 0);
+      issue_s(0);
+      for (int i = 0; i < T; ++i) {
+        const int st = i & 1;
+        mbar_wait(&bars->pds_full, i & 1);  // P^T, dS^T of tile i are in smem; S^T / dP^T have been read
+        tc_fence_after_sync();
+        if (i + 1 < T) issue_s(i + 1);      // next tile's scores first: the warpgroups can start on them
+        if (i >= 1) {
+          mbar_wait(&bars->dq_empty, (i - 1) & 1);  // dQ_{i-1} has been drained from TMEM
+          tc_fence_after_sync();
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // K = 128 query rows
+          const uint64_t a_pt = desc_kmajor<128>(pt_addr + (ks >> 2) * 16384, (ks & 3) * 32);
+          const uint64_t b_do = desc_mnmajor<SW>(do_addr + st * Cfg::TILE_BYTES, ks * 16, Cfg::BOX_BYTES);
+          mma_ss(tmem + Cfg::TMEM_DV, a_pt, b_do, idesc_kv, (i > 0) || (ks > 0));
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a_ds = desc_kmajor<128>(dst_addr + (ks >> 2) * 16384, (ks & 3) * 32);
+          const uint64_t b_q = desc_mnmajor<SW>(q_addr + st * Cfg::TILE_BYTES, ks * 16, Cfg::BOX_BYTES);
+          mma_ss(tmem + Cfg::TMEM_DK, a_ds, b_q, idesc_kv, (i > 0) || (ks > 0));
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // K = 128 key rows
+          const uint64_t a_ds = desc_mnmajor<128>(dst_addr, ks * 16, 16384);
+          const uint64_t b_k = desc_mnmajor<SW>(k_addr, ks * 16, Cfg::BOX_BYTES);
+          mma_ss(tmem + Cfg::TMEM_DQ, a_ds, b_k, idesc_dq, ks > 0);
+        }
+        mma_commit(&bars->q_empty[st]);
+        mma_commit(&bars->pds_empty);
+        mma_commit(&bars->dq_full);
+      }
+      mma_commit(&bars->fin_full);
+    }
+  } else if (warp >= 4) {
+    // ---------------- elementwise warpgroups ----------------
+    const int wg = (warp - 4) >> 2;                // owns query columns [64*wg, 64*wg + 64) of every tile
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;              // key row inside the tile == TMEM lane
+    const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
+    const int j_pos = n0 + row;
+    const float ah = p.alpha_half;
+    const bool fast = msk.fast != 0;
+    const bool j_ok = j_pos < len;
+    const bool j_hist = j_ok && (!msk.has_tgt || j_pos < msk.max_id);  // fast mask: valid = (j_hist & i > j) | (i == j)
+    uint8_t* sPTw = sPT + wg * 16384;
+    uint8_t* sDSTw = sDST + wg * 16384;
+    const int cbase = wg * 64;
+    const int qcol0 = wg * (D / 2);                // dQ columns drained by this warpgroup
+
+    auto drain_dq = [&](int i) {
+      // dQ tile of query tile i: TMEM lane = query row -> fp32 vector reductions into dq_acc
+      mbar_wait(&bars->dq_full, i & 1);
+      tc_fence_after_sync();
+      const int qpos = q_tile(i) * 128 + row;
+      float* dst = p.dq_acc + ((row0 + qpos) * p.heads + h) * (long long)D + qcol0;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t r[16];
+        tmem_ld16(tmem + Cfg::TMEM_DQ + qcol0 + c * 16 + lane_bits, r);
+        tmem_ld_wait();
+        if (qpos < len) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            red_add_v4(dst + c * 16 + e, __uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]),
+                       __uint_as_float(r[e + 3]));
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&bars->dq_empty);
+    };
+
+    for (int i = 0; i < T; ++i) {
+      const int m0 = q_tile(i) * 128;
+      mbar_wait(&bars->s_full, i & 1);
+      tc_fence_after_sync();
+      // tile-uniform classification
+      const bool full = fast && (m0 >= n0 + 128) && (m0 + 128 <= len) && (!msk.has_tgt || n0 + 128 <= msk.max_id);
+      const int mode = full ? 0 : (fast ? 1 : 2);
+      const int jr = j_pos - m0 - cbase;           // query column (relative to this warpgroup's block) equal to j
+      const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
+      const uint32_t st_addr = tmem + Cfg::TMEM_ST + cbase + lane_bits;
+      const uint32_t dp_addr = tmem + Cfg::TMEM_DPT + cbase + lane_bits;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {  // 2 chunks of 32 query columns
+        uint32_t s[32], dp[32];
+        tmem_ld32(st_addr + c * 32, s);
+        tmem_ld32(dp_addr + c * 32, dp);
+        tmem_ld_wait();
+        uint32_t pp[16], dd[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float hh = __uint_as_float(s[e + u]) * ah;
+            const float t = tanh_approx(hh);
+            const float pval = fmaf(hh, t, hh);           // x * sigmoid(x), x = 2 hh
+            const float sig = fmaf(0.5f, t, 0.5f);
+            const float onem = fmaf(-0.5f, t, 0.5f);      // 1 - sigmoid
+            const float g = fmaf(pval, onem, sig);        // sig * (1 + x (1 - sig))
+            float dsv = __uint_as_float(dp[e + u]) * g;
+            float pvv = pval;
+            if (mode != 0) {
+              const int cq = c * 32 + e + u;              // query column within this warpgroup's 64
+              bool valid;
+              if (mode == 1) {
+                valid = ((j_hist & (cq > jr)) | (cq == jr)) & (cq < len_rel) & j_ok;
+              } else {
+                const int i_pos = m0 + cbase + cq;
+                valid = j_ok && i_pos < len && mask_valid(msk, i_pos, j_pos);
+              }
+              pvv = valid ? pvv : 0.f;
+              dsv = valid ? dsv : 0.f;
+            }
+            pv[u] = pvv;
+            dv[u] = dsv;
+          }
+          pp[e >> 1] = BF16 ? pack_bf16x2(pv[0], pv[1]) : pack_f16x2(pv[0], pv[1]);
+          dd[e >> 1] = BF16 ? pack_bf16x2(dv[0], dv[1]) : pack_f16x2(dv[0], dv[1]);
+        }
+        if (c == 0 && i >= 1) mbar_wait(&bars->pds_empty, (i - 1) & 1);  // previous tile's GEMMs are done with P^T/dS^T
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const uint32_t off = swizzled_chunk_offset<128>(row, c * 4 + j4);
+          *reinterpret_cast<uint4*>(sPTw + off) = make_uint4(pp[4 * j4], pp[4 * j4 + 1], pp[4 * j4 + 2], pp[4 * j4 + 3]);
+          *reinterpret_cast<uint4*>(sDSTw + off) = make_uint4(dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->pds_full);
+      if (i >= 1) drain_dq(i - 1);
+    }
+    drain_dq(T - 1);
+    // ---------------- epilogue: dV (warpgroup 0) / dK (warpgroup 1): TMEM -> scale -> global ----------------
+    mbar_wait(&bars->fin_full, 0);
+    tc_fence_after_sync();
+    const uint32_t acc = tmem + (wg == 0 ? Cfg::TMEM_DV : Cfg::TMEM_DK) + lane_bits;
+    const float scale = wg == 0 ? p.dv_scale : p.dk_scale;
+    uint16_t* gptr = wg == 0
+        ? reinterpret_cast<uint16_t*>(p.dv) + (row0 + j_pos) * p.dv_row_stride + (long long)h * p.dv_head_stride
+        : reinterpret_cast<uint16_t*>(p.dk) + (row0 + j_pos) * p.dk_row_stride + (long long)h * p.dk_head_stride;
+#pragma unroll
+    for (int c = 0; c < D / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld16(acc + c * 16, o);
+      tmem_ld_wait();
+      if (j_ok) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          const float a = __uint_as_float(o[e]) * scale, bb = __uint_as_float(o[e + 1]) * scale;
+          pk[e >> 1] = BF16 ? pack_bf16x2(a, bb) : pack_f16x2(a, bb);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(gptr + c * 16);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// dq[r, h, :] = convert(dq_acc[r, h, :] * scale)
+template <bool BF16>
+__global__ void dq_convert_kernel(const float* __restrict__ acc, uint16_t* __restrict__ dq, long long rows, int heads, int D,
+                                  long long row_stride, long long head_stride, float scale) {
+  const long long nvec = rows * heads * (D / 8);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % (D / 8));
+    const long long rh = idx / (D / 8);
+    const int hh = (int)(rh % heads);
+    const long long r = rh / heads;
+    const float4 a = *reinterpret_cast<const float4*>(acc + rh * D + v * 8);
+    const float4 c = *reinterpret_cast<const float4*>(acc + rh * D + v * 8 + 4);
+    uint4 o;
+    if (BF16) {
+      o = make_uint4(pack_bf16x2(a.x * scale, a.y * scale), pack_bf16x2(a.z * scale, a.w * scale),
+                     pack_bf16x2(c.x * scale, c.y * scale), pack_bf16x2(c.z * scale, c.w * scale));
+    } else {
+      o = make_uint4(pack_f16x2(a.x * scale, a.y * scale), pack_f16x2(a.z * scale, a.w * scale),
+                     pack_f16x2(c.x * scale, c.y * scale), pack_f16x2(c.z * scale, c.w * scale));
+    }
+    *reinterpret_cast<uint4*>(dq + r * row_stride + hh * head_stride + v * 8) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+static bool aligned_view(const void* ptr, long long row_stride, long long head_stride) {
+  return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (row_stride % 8) == 0 && (head_stride % 8) == 0;
+}
+
+static bool umma_bwd_supported(const hstu_attn_params& p) {
+  if (!umma_fwd_supported(p)) return false;  // dtype / dims / alignment of q, k, v (out is not used by the backward)
+  if (p.dqk != 32 && p.dqk != 64) return false;
+  return aligned_view(p.dout, p.do_row_stride, p.do_head_stride) && aligned_view(p.dq, p.dq_row_stride, p.dq_head_stride) &&
+         aligned_view(p.dk, p.dk_row_stride, p.dk_head_stride) && aligned_view(p.dv_out, p.dv_row_stride, p.dv_head_stride);
+}
+
 bool umma_supported(const hstu_attn_params& p, bool bwd) {
-  if (bwd) return false;  // tcgen05 backward not enabled yet: the generic kernels run the backward
-  return umma_fwd_supported(p);
+  if (!bwd) return umma_fwd_supported(p);
+  hstu_attn_params q = p;
+  if (q.out == nullptr) q.out = const_cast<void*>(q.q);  // the forward check also looks at `out`
+  q.o_row_stride = 8;
+  q.o_head_stride = 8;
+  return umma_bwd_supported(q);
 }
 
 size_t umma_workspace_bytes(const hstu_attn_params& p, bool bwd) {
-  (void)p;
-  (void)bwd;
+  if (!bwd) return 0;
+  return (size_t)p.total_rows * p.heads * p.dqk * sizeof(float);
+}
+
+template <int D, bool BF16>
+static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
+  using Cfg = BwdCfg<D>;
+  const size_t need = umma_workspace_bytes(p, true);
+  if (p.workspace == nullptr || p.workspace_bytes < need) {
+    set_error("hstu_attn_bwd: workspace of %zu bytes required (got %zu)", need, p.workspace_bytes);
+    return HSTU_ERR_WORKSPACE;
+  }
+  BwdParams bp;
+  memset(&bp, 0, sizeof(bp));
+  if (int e = make_tmap_rows_heads(&bp.tmQ, p.q, p.total_rows, p.heads, D, p.q_row_stride, p.q_head_stride, Cfg::BOX_COLS, 128)) return e;
+  if (int e = make_tmap_rows_heads(&bp.tmK, p.k, p.total_rows, p.heads, D, p.k_row_stride, p.k_head_stride, Cfg::BOX_COLS, 128)) return e;
+  if (int e = make_tmap_rows_heads(&bp.tmV, p.v, p.total_rows, p.heads, D, p.v_row_stride, p.v_head_stride, Cfg::BOX_COLS, 128)) return e;
+  if (int e = make_tmap_rows_heads(&bp.tmDO, p.dout, p.total_rows, p.heads, D, p.do_row_stride, p.do_head_stride, Cfg::BOX_COLS, 128)) return e;
+  bp.seq_offsets = p.seq_offsets;
+  bp.num_targets = p.num_targets;
+  bp.dk = p.dk;
+  bp.dv = p.dv_out;
+  bp.dq_acc = reinterpret_cast<float*>(p.workspace);
+  bp.dk_row_stride = p.dk_row_stride;
+  bp.dk_head_stride = p.dk_head_stride;
+  bp.dv_row_stride = p.dv_row_stride;
+  bp.dv_head_stride = p.dv_head_stride;
+  bp.offsets_i64 = p.offsets_are_i64;
+  bp.targets_i64 = p.num_targets_are_i64;
+  bp.max_seq_len = p.max_seq_len;
+  bp.heads = p.heads;
+  bp.win = p.max_attn_len;
+  bp.min_full = p.min_full_attn_seq_len;
+  bp.ctx = p.contextual_seq_len;
+  bp.alpha_half = 0.5f * p.alpha;
+  bp.dv_scale = 1.0f / (float)p.max_seq_len;
+  bp.dk_scale = p.alpha / (float)p.max_seq_len;
+  HSTU_CUDA_OK(cudaMemsetAsync(p.workspace, 0, need, st));
+  auto kern = attn_bwd_umma_kernel<D, BF16>;
+  HSTU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  dim3 grid((p.max_seq_len + 127) / 128, p.heads, p.batch);
+  kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(bp);
+  HSTU_CUDA_OK(cudaGetLastError());
+  const long long nvec = p.total_rows * p.heads * (D / 8);
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dq_convert_kernel<BF16><<<(int)blocks, 256, 0, st>>>(bp.dq_acc, reinterpret_cast<uint16_t*>(p.dq), p.total_rows, p.heads, D,
+                                                       p.dq_row_stride, p.dq_head_stride, bp.dk_scale);
+  HSTU_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int attn_umma_bwd(const hstu_attn_params& p, cudaStream_t st) {
-  (void)p;
-  (void)st;
-  set_error("tcgen05 backward is not available in this build");
+  const bool bf = p.dtype == HSTU_BF16;
+  switch (p.dqk) {
+    case 32: return bf ? launch_bwd_umma<32, true>(p, st) : launch_bwd_umma<32, false>(p, st);
+    case 64: return bf ? launch_bwd_umma<64, true>(p, st) : launch_bwd_umma<64, false>(p, st);
+  }
+  set_error("tcgen05 backward: unsupported head dim %d", p.dqk);
   return HSTU_ERR_UNSUPPORTED;
 }
 

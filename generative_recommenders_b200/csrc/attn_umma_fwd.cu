@@ -191,31 +191,54 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
     const int i_pos = m0 + row;
     const float ah = p.alpha_half;
-    const int full_lim = msk.fast ? min(m0, msk.has_tgt ? msk.max_id : 0x7fffffff) : -1;
+    const bool fast = msk.fast != 0;
+    // plain causal (+targets): valid(i, j) = (j < lim_i) | (j == i)   (common.cuh: mask_valid, fast path)
+    const int lim_i = msk.has_tgt ? min(i_pos, msk.max_id) : i_pos;
+    const int full_lim = fast ? min(m0, msk.has_tgt ? msk.max_id : 0x7fffffff) : -1;
     uint8_t* sPw = sP + wg * Cfg::P_BYTES;
+    const uint32_t s_taddr = tmem + Cfg::TMEM_S + wg * 128 + lane_bits;
     for (int i = wg, it = 0; i < T; i += 2, ++it) {
       mbar_wait(&bars->s_full[wg], it & 1);
       tc_fence_after_sync();
       if (it >= 1) mbar_wait(&bars->p_empty[wg], (it - 1) & 1);
       const int n0 = (t0 + i) * 128;
-      const bool full = (n0 + 128 <= full_lim);
+      const int mode = (n0 + 128 <= full_lim) ? 0 : (fast ? 1 : 2);  // tile-uniform: no divergence
+      const int lim_rel = lim_i - n0, diag_rel = i_pos - n0;
+      uint32_t sbuf[2][32];
+      tmem_ld32(s_taddr, sbuf[0]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld32(tmem + Cfg::TMEM_S + wg * 128 + c * 32 + lane_bits, s);
         tmem_ld_wait();
+        if (c < 3) tmem_ld32(s_taddr + (c + 1) * 32, sbuf[(c + 1) & 1]);  // prefetch the next 32 columns
+        const uint32_t(&s)[32] = sbuf[c & 1];
         uint32_t pk[16];
+        if (mode == 0) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float h0 = __uint_as_float(s[e]) * ah, h1 = __uint_as_float(s[e + 1]) * ah;
-          float p0 = fmaf(h0, tanh_approx(h0), h0);
-          float p1 = fmaf(h1, tanh_approx(h1), h1);
-          if (!full) {
+          for (int e = 0; e < 32; e += 2) {
+            const float h0 = __uint_as_float(s[e]) * ah, h1 = __uint_as_float(s[e + 1]) * ah;
+            const float p0 = fmaf(h0, tanh_approx(h0), h0), p1 = fmaf(h1, tanh_approx(h1), h1);
+            pk[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+          }
+        } else if (mode == 1) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const int j0 = c * 32 + e;
+            const float h0 = __uint_as_float(s[e]) * ah, h1 = __uint_as_float(s[e + 1]) * ah;
+            float p0 = fmaf(h0, tanh_approx(h0), h0), p1 = fmaf(h1, tanh_approx(h1), h1);
+            p0 = ((j0 < lim_rel) | (j0 == diag_rel)) ? p0 : 0.f;
+            p1 = ((j0 + 1 < lim_rel) | (j0 + 1 == diag_rel)) ? p1 : 0.f;
+            pk[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
             const int j = n0 + c * 32 + e;
+            const float h0 = __uint_as_float(s[e]) * ah, h1 = __uint_as_float(s[e + 1]) * ah;
+            float p0 = fmaf(h0, tanh_approx(h0), h0), p1 = fmaf(h1, tanh_approx(h1), h1);
             p0 = (j < len && mask_valid(msk, i_pos, j)) ? p0 : 0.f;
             p1 = (j + 1 < len && mask_valid(msk, i_pos, j + 1)) ? p1 : 0.f;
+            pk[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
           }
-          pk[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
         }
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {

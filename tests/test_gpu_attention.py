@@ -48,7 +48,7 @@ def test_attention_golden(fname):
     for impl in impls:
         out, dq, dk, dv = _run(g, impl)
         for name, a in (("out", out), ("dq", dq), ("dk", dk), ("dv", dv)):
-            assert_rel(a, ref[name], f"{fname}:{name}:impl{impl}")
+            assert_rel(a, ref[name], f"{fname}:{name}:impl{impl}", operand_roundings=int(impl != _lib.IMPL_GENERIC))
         # the reference's own criterion (hstu_attention_test.py:152-163): assert_close vs eager in the native dtype
         nat = g["ref_native"]
         torch.testing.assert_close(out.cpu(), nat["out"])
@@ -71,7 +71,7 @@ def _random_case(seed, dtype, B, H, max_uih, max_tgt, dqk, dv, targets, window, 
     return case
 
 
-def _check_vs_oracle(case, impl, tag):
+def _check_vs_oracle(case, impl, tag, operand_roundings=0):
     kw = dict(num_targets=case["num_targets"], max_attn_len=case["max_attn_len"],
               contextual_seq_len=case["contextual_seq_len"], min_full_attn_seq_len=case["min_full_attn_seq_len"])
     ref_out = O.hstu_mha_fwd(case["max_seq_len"], case["alpha"], case["q"], case["k"], case["v"], case["seq_offsets"], **kw)
@@ -79,7 +79,7 @@ def _check_vs_oracle(case, impl, tag):
                                    case["seq_offsets"], **kw)
     out, dq, dk, dv = _run(case, impl)
     for name, a, r in (("out", out, ref_out), ("dq", dq, rdq), ("dk", dk, rdk), ("dv", dv, rdv)):
-        assert_rel(a, r, f"{tag}:{name}")
+        assert_rel(a, r, f"{tag}:{name}", operand_roundings=operand_roundings)
 
 
 GRID = list(itertools.product([torch.float32, torch.bfloat16], [(20, 20), (100, 20), (128, 512), (256, 20)],
@@ -105,7 +105,7 @@ def test_attention_umma_vs_oracle(d, dtype, opts):
     _lib = _mods()[0]
     targets, window, ctx, min_full = opts
     case = _random_case(7000 + d + ctx, dtype, 5, 3, 300, 24, d, d, targets, window, ctx, min_full)
-    _check_vs_oracle(case, _lib.IMPL_AUTO, f"umma-d{d}-{dtype}-{opts}")
+    _check_vs_oracle(case, _lib.IMPL_AUTO, f"umma-d{d}-{dtype}-{opts}", operand_roundings=1)
 
 
 def test_attention_strided_views_and_empty():
@@ -121,7 +121,7 @@ def test_attention_strided_views_and_empty():
     for impl in (_lib.IMPL_GENERIC, _lib.IMPL_AUTO):
         out = hstu_mha(300, 1.0 / d, q, k, v, off, kernel=HK.CUDA, impl=impl)
         ref = O.hstu_mha_fwd(300, 1.0 / d, q.cpu(), k.cpu(), v.cpu(), off.cpu())
-        assert_rel(out, ref, f"strided impl{impl}")
+        assert_rel(out, ref, f"strided impl{impl}", operand_roundings=int(impl != _lib.IMPL_GENERIC))
     e = torch.empty(0, H, d, device=dev, dtype=torch.bfloat16)
     out = hstu_mha(16, 0.1, e, e, e, torch.zeros(3, dtype=torch.int64, device=dev), kernel=HK.CUDA)
     assert out.shape == (0, H, d)
@@ -176,4 +176,4 @@ def test_target_invariance_metamorphic():
     for impl in (_lib.IMPL_GENERIC, _lib.IMPL_AUTO):
         o1 = hstu_mha(256, 0.2, q, k, v, off, num_targets=nt, kernel=HK.CUDA, impl=impl)
         o2 = hstu_mha(256, 0.2, q[perm], k[perm], v[perm], off, num_targets=nt, kernel=HK.CUDA, impl=impl)
-        assert_rel(o2, o1[perm].float(), f"target invariance impl {impl}", tol=2e-3)
+        assert_rel(o2, o1[perm].float(), f"target invariance impl {impl}", tol=2e-3, operand_roundings=1)

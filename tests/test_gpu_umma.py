@@ -51,7 +51,16 @@ def test_umma_matches_generic_at_full_size(d, lmax, B, H):
     o_ref = hstu_mha(lmax, alpha, q.float(), k.float(), v.float(), off, num_targets=nt, kernel=HammerKernel.CUDA,
                      impl=_lib.IMPL_GENERIC)
     o = hstu_mha(lmax, alpha, q, k, v, off, num_targets=nt, kernel=HammerKernel.CUDA, impl=_lib.IMPL_UMMA)
-    assert_rel(o, o_ref, f"umma vs generic d={d} lmax={lmax}")
+    assert_rel(o, o_ref, f"umma vs generic d={d} lmax={lmax}", operand_roundings=1)
+    # backward: tcgen05 (where supported) vs the CUDA-core kernels on the same bf16 inputs
+    do = torch.randn_like(o)
+    grads = {}
+    for impl in (_lib.IMPL_GENERIC, _lib.IMPL_AUTO):
+        qq, kk, vv = (t.detach().clone().requires_grad_() for t in (q, k, v))
+        hstu_mha(lmax, alpha, qq, kk, vv, off, num_targets=nt, kernel=HammerKernel.CUDA, impl=impl).backward(do)
+        grads[impl] = (qq.grad, kk.grad, vv.grad)
+    for name, a, r in zip(("dq", "dk", "dv"), grads[_lib.IMPL_AUTO], grads[_lib.IMPL_GENERIC]):
+        assert_rel(a, r.float(), f"bwd umma vs generic {name} d={d} lmax={lmax}", tol=2e-3, operand_roundings=2)
 
 
 def test_linearity_in_v_and_sequence_permutation():
