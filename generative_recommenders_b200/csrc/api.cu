@@ -41,6 +41,22 @@ static int validate_attn(const hstu_attn_params* p, bool bwd) {
   return 0;
 }
 
+// Make the device that owns `ptr` current on the calling thread.  The caller may be a thread that has never touched
+// CUDA (e.g. the autograd engine thread): kernels must go to the device of the data, and driver-API calls such as
+// cuTensorMapEncodeTiled need a current context.
+int bind_device(const void* ptr) {
+  if (ptr == nullptr) return 0;  // empty tensor: nothing will be launched
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
+  if (e != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+    cudaGetLastError();
+    set_error("expected a CUDA device pointer (got %p: %s)", ptr, e == cudaSuccess ? "host memory" : cudaGetErrorString(e));
+    return HSTU_ERR_INVALID_ARGUMENT;
+  }
+  HSTU_CUDA_OK(cudaSetDevice(attr.device));
+  return 0;
+}
+
 static int select_impl(const hstu_attn_params* p, bool bwd) {
   const bool can = umma_supported(*p, bwd);
   if (p->impl == HSTU_IMPL_GENERIC) return HSTU_IMPL_GENERIC;
@@ -81,6 +97,7 @@ size_t hstu_attn_workspace_bytes(const hstu_attn_params* p, int is_backward) {
 int hstu_attn_fwd(const hstu_attn_params* p, void* stream) {
   if (int e = validate_attn(p, false)) return e;
   if (p->batch == 0 || p->total_rows == 0) return 0;  // triton_hstu_attention.py:1789-1790
+  if (int e = bind_device(p->q)) return e;
   int impl = select_impl(p, false);
   if (impl < 0) return impl;
   if (impl == HSTU_IMPL_UMMA) return attn_umma_fwd(*p, (cudaStream_t)stream);
@@ -90,6 +107,7 @@ int hstu_attn_fwd(const hstu_attn_params* p, void* stream) {
 int hstu_attn_bwd(const hstu_attn_params* p, void* stream) {
   if (int e = validate_attn(p, true)) return e;
   if (p->batch == 0 || p->total_rows == 0) return 0;
+  if (int e = bind_device(p->q)) return e;
   int impl = select_impl(p, true);
   if (impl < 0) return impl;
   if (impl == HSTU_IMPL_UMMA) return attn_umma_bwd(*p, (cudaStream_t)stream);
@@ -129,6 +147,7 @@ int hstu_q_range_for_kv_rows(int32_t len, int32_t num_targets, int32_t max_attn_
 int hstu_layer_norm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t n_rows,
                         int32_t D, int64_t x_row_stride, int64_t y_row_stride, float eps, int32_t dtype, int32_t swish,
                         void* stream) {
+  if (n_rows > 0) if (int e = bind_device(x)) return e;
   HSTU_CHECK_ARG(n_rows >= 0 && (n_rows == 0 || (x && y)), "layer_norm_fwd: NULL x/y");
   return layer_norm_fwd(x, w, b, y, mean, rstd, n_rows, D, x_row_stride, y_row_stride, eps, dtype, swish, false,
                         (cudaStream_t)stream);
@@ -137,6 +156,7 @@ int hstu_layer_norm_fwd(const void* x, const void* w, const void* b, void* y, fl
 int hstu_layer_norm_bwd(const void* dy, const void* x, const void* w, const void* b, const float* mean, const float* rstd,
                         void* dx, float* dw, float* db, float* partial, int64_t n_rows, int32_t D, int64_t x_row_stride,
                         int64_t dy_row_stride, int64_t dx_row_stride, int32_t dtype, int32_t swish, void* stream) {
+  if (n_rows > 0) if (int e = bind_device(x)) return e;
   HSTU_CHECK_ARG(n_rows >= 0 && (n_rows == 0 || (dy && x && dx && mean && rstd)), "layer_norm_bwd: NULL argument");
   return layer_norm_bwd(dy, x, w, b, mean, rstd, dx, dw, db, partial, n_rows, D, x_row_stride, dy_row_stride,
                         dx_row_stride, dtype, swish, false, (cudaStream_t)stream);
@@ -146,12 +166,14 @@ int32_t hstu_norm_bwd_partial_rows(void) { return norm_partial_rows(); }
 
 int hstu_rms_norm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t n_rows, int32_t D, float eps,
                       int32_t dtype, void* stream) {
+  if (n_rows > 0) if (int e = bind_device(x)) return e;
   HSTU_CHECK_ARG(n_rows >= 0 && (n_rows == 0 || (x && y && w)), "rms_norm_fwd: NULL argument");
   return layer_norm_fwd(x, w, nullptr, y, nullptr, rstd, n_rows, D, D, D, eps, dtype, 0, true, (cudaStream_t)stream);
 }
 
 int hstu_rms_norm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw,
                       float* partial, int64_t n_rows, int32_t D, int32_t dtype, void* stream) {
+  if (n_rows > 0) if (int e = bind_device(x)) return e;
   HSTU_CHECK_ARG(n_rows >= 0 && (n_rows == 0 || (dy && x && w && dx && rstd)), "rms_norm_bwd: NULL argument");
   return layer_norm_bwd(dy, x, w, nullptr, nullptr, rstd, dx, dw, nullptr, partial, n_rows, D, D, D, D, dtype, 0, true,
                         (cudaStream_t)stream);
@@ -161,6 +183,7 @@ int hstu_norm_mul_dropout_fwd(const void* attn, const void* u, const void* w, co
                               float* rstd, int64_t n_rows, int32_t heads, int32_t dv, int64_t attn_row_stride,
                               int64_t u_row_stride, float eps, float dropout_p, uint64_t seed, int32_t dtype,
                               int32_t silu_u, int32_t concat_ux, int32_t group_norm, void* stream) {
+  if (n_rows > 0) if (int e = bind_device(attn)) return e;
   HSTU_CHECK_ARG(n_rows >= 0 && (n_rows == 0 || (attn && u && w && b && out)), "norm_mul_dropout_fwd: NULL argument");
   HSTU_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p must be in [0, 1)");
   return norm_mul_dropout_fwd(attn, u, w, b, out, mean, rstd, n_rows, heads, dv, attn_row_stride, u_row_stride, eps,
@@ -173,6 +196,7 @@ int hstu_norm_mul_dropout_bwd(const void* dout, const void* attn, const void* u,
                               int64_t u_row_stride, int64_t dattn_row_stride, int64_t du_row_stride, float dropout_p,
                               uint64_t seed, int32_t dtype, int32_t silu_u, int32_t concat_ux, int32_t group_norm,
                               void* stream) {
+  if (n_rows > 0) if (int e = bind_device(attn)) return e;
   HSTU_CHECK_ARG(n_rows >= 0 && (n_rows == 0 || (dout && attn && u && w && b && mean && rstd && dattn && du)),
                  "norm_mul_dropout_bwd: NULL argument");
   return norm_mul_dropout_bwd(dout, attn, u, w, b, mean, rstd, dattn, du, dw, db, partial, n_rows, heads, dv,
@@ -182,12 +206,14 @@ int hstu_norm_mul_dropout_bwd(const void* dout, const void* attn, const void* u,
 
 int hstu_silu_fwd(const void* x, void* y, int64_t n_rows, int32_t n_cols, int64_t x_row_stride, int64_t y_row_stride,
                   int32_t dtype, void* stream) {
+  if (n_rows > 0) if (int e = bind_device(x)) return e;
   HSTU_CHECK_ARG(n_rows >= 0 && (n_rows == 0 || (x && y)), "silu_fwd: NULL argument");
   return silu_fwd_bwd(x, nullptr, y, n_rows, n_cols, x_row_stride, 0, y_row_stride, dtype, false, (cudaStream_t)stream);
 }
 
 int hstu_silu_bwd(const void* dy, const void* x, void* dx, int64_t n_rows, int32_t n_cols, int64_t dy_row_stride,
                   int64_t x_row_stride, int64_t dx_row_stride, int32_t dtype, void* stream) {
+  if (n_rows > 0) if (int e = bind_device(x)) return e;
   HSTU_CHECK_ARG(n_rows >= 0 && (n_rows == 0 || (dy && x && dx)), "silu_bwd: NULL argument");
   return silu_fwd_bwd(x, dy, dx, n_rows, n_cols, x_row_stride, dy_row_stride, dx_row_stride, dtype, true,
                       (cudaStream_t)stream);
@@ -196,6 +222,7 @@ int hstu_silu_bwd(const void* dy, const void* x, void* dx, int64_t n_rows, int32
 int hstu_jagged_concat(const void* left, const void* right, void* out, const void* offsets_left, const void* offsets_right,
                        int32_t offsets_are_i64, int32_t batch, int32_t dense_len_left, int32_t dense_len_right,
                        int32_t n_prefix, int32_t D, int32_t elem_bytes, int32_t max_seq_len, void* stream) {
+  if (int e = bind_device(out)) return e;
   HSTU_CHECK_ARG(offsets_left || offsets_right, "offsets_left and offsets_right cannot be None at the same time");
   HSTU_CHECK_ARG(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4 || elem_bytes == 8, "bad elem_bytes");
   return jagged_concat_split(false, left, right, out, nullptr, offsets_left, offsets_right, offsets_are_i64, batch,
@@ -205,6 +232,7 @@ int hstu_jagged_concat(const void* left, const void* right, void* out, const voi
 int hstu_jagged_split(const void* in, void* left, void* right, const void* offsets_left, const void* offsets_right,
                       int32_t offsets_are_i64, int32_t batch, int32_t dense_len_left, int32_t dense_len_right,
                       int32_t n_prefix, int32_t D, int32_t elem_bytes, int32_t max_seq_len, void* stream) {
+  if (int e = bind_device(in)) return e;
   HSTU_CHECK_ARG(offsets_left || offsets_right, "offsets_left and offsets_right cannot be None at the same time");
   HSTU_CHECK_ARG(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4 || elem_bytes == 8, "bad elem_bytes");
   return jagged_concat_split(true, in, nullptr, left, right, offsets_left, offsets_right, offsets_are_i64, batch,

@@ -272,37 +272,58 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         tmem_ld32(dp_addr + c * 32, dp);
         tmem_ld_wait();
         uint32_t pp[16], dd[16];
+        // p = x sig(x) and g = sig (1 + x (1 - sig)) from one tanh: x = 2 hh, sig = (1 + t) / 2
+#define HSTU_BWD_ELEM(E, PV, DV)                                   \
+  {                                                                \
+    const float hh = __uint_as_float(s[E]) * ah;                   \
+    const float t = tanh_approx(hh);                               \
+    PV = fmaf(hh, t, hh);                                          \
+    const float sig = fmaf(0.5f, t, 0.5f);                         \
+    const float onem = fmaf(-0.5f, t, 0.5f);                       \
+    DV = __uint_as_float(dp[E]) * fmaf(PV, onem, sig);             \
+  }
+        if (mode == 0) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float pv[2], dv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float hh = __uint_as_float(s[e + u]) * ah;
-            const float t = tanh_approx(hh);
-            const float pval = fmaf(hh, t, hh);           // x * sigmoid(x), x = 2 hh
-            const float sig = fmaf(0.5f, t, 0.5f);
-            const float onem = fmaf(-0.5f, t, 0.5f);      // 1 - sigmoid
-            const float g = fmaf(pval, onem, sig);        // sig * (1 + x (1 - sig))
-            float dsv = __uint_as_float(dp[e + u]) * g;
-            float pvv = pval;
-            if (mode != 0) {
-              const int cq = c * 32 + e + u;              // query column within this warpgroup's 64
-              bool valid;
-              if (mode == 1) {
-                valid = ((j_hist & (cq > jr)) | (cq == jr)) & (cq < len_rel) & j_ok;
-              } else {
-                const int i_pos = m0 + cbase + cq;
-                valid = j_ok && i_pos < len && mask_valid(msk, i_pos, j_pos);
-              }
-              pvv = valid ? pvv : 0.f;
-              dsv = valid ? dsv : 0.f;
-            }
-            pv[u] = pvv;
-            dv[u] = dsv;
+          for (int e = 0; e < 32; e += 2) {
+            float p0, p1, d0, d1;
+            HSTU_BWD_ELEM(e, p0, d0);
+            HSTU_BWD_ELEM(e + 1, p1, d1);
+            pp[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+            dd[e >> 1] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
           }
-          pp[e >> 1] = BF16 ? pack_bf16x2(pv[0], pv[1]) : pack_f16x2(pv[0], pv[1]);
-          dd[e >> 1] = BF16 ? pack_bf16x2(dv[0], dv[1]) : pack_f16x2(dv[0], dv[1]);
+        } else if (mode == 1) {
+          // valid(i, j) = ((j is history) & (i > j)) | (i == j), restricted to i < len and j < len
+          const int lo_c = j_hist ? jr : 0x7fffffff;       // columns > lo_c are valid (if j is a history position)
+          const int dg_c = j_ok ? jr : -0x7fffffff;        // the diagonal column
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0, p1, d0, d1;
+            HSTU_BWD_ELEM(e, p0, d0);
+            HSTU_BWD_ELEM(e + 1, p1, d1);
+            const int c0 = c * 32 + e;
+            const bool v0 = ((c0 > lo_c) | (c0 == dg_c)) & (c0 < len_rel);
+            const bool v1 = ((c0 + 1 > lo_c) | (c0 + 1 == dg_c)) & (c0 + 1 < len_rel);
+            p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;
+            p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;
+            pp[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+            dd[e >> 1] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0, p1, d0, d1;
+            HSTU_BWD_ELEM(e, p0, d0);
+            HSTU_BWD_ELEM(e + 1, p1, d1);
+            const int i_pos = m0 + cbase + c * 32 + e;
+            const bool v0 = j_ok && i_pos < len && mask_valid(msk, i_pos, j_pos);
+            const bool v1 = j_ok && i_pos + 1 < len && mask_valid(msk, i_pos + 1, j_pos);
+            p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;
+            p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;
+            pp[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+            dd[e >> 1] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
+          }
         }
+#undef HSTU_BWD_ELEM
         if (c == 0 && i >= 1) mbar_wait(&bars->pds_empty, (i - 1) & 1);  // previous tile's GEMMs are done with P^T/dS^T
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {

@@ -5,7 +5,7 @@
 //   warp 0  lane 0 : TMA producer for Q (once) and the K tiles          (2-stage ring, mbarrier full/empty)
 //   warp 3  lane 0 : TMA producer for the V tiles                      (2-stage ring)
 //   warp 1  lane 0 : tcgen05.mma issuer:  S_t = Q K_t^T  (SS, both K-major)  and  O += P_t V_t  (A = P in smem,
-//                    B = V MN-major), S double-buffered in TMEM, O accumulated in TMEM across all key tiles
+//                    B = V MN-major), S in a 3-deep TMEM ring, O accumulated in TMEM across all key tiles
 //   warp 2         : TMEM allocation / release
 //   warps 4-7, 8-11: two "silu" warpgroups.  Warpgroup g owns key tiles t = g, g+2, ...: tcgen05.ld S (one query row per
 //                    thread), p = silu(alpha*s) * mask via one MUFU (tanh) + 2 FMA-pipe ops, packs bf16 pairs and writes
@@ -51,14 +51,15 @@ struct FwdCfg {
   static constexpr int OFF_P = OFF_V + STAGES * TILE_BYTES;
   static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
-  static constexpr int TMEM_S = 0;      // S buffers: columns [0,128) and [128,256)
-  static constexpr int TMEM_O = 256;    // O accumulator: columns [256, 256 + D)
+  static constexpr int TMEM_S = 0;      // ring of 3 S buffers: columns [0,128), [128,256), [256,384)
+  static constexpr int TMEM_O = 384;    // O accumulator: columns [384, 384 + D)
+  static_assert(384 + D <= 512, "TMEM budget");
 };
 
 struct FwdBars {
   uint64_t q_full;
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
-  uint64_t s_full[2], p_full[2], p_empty[2];
+  uint64_t s_full[3], p_full[2], p_empty[2];
   uint64_t o_full;
   uint32_t tmem_base;
 };
@@ -97,10 +98,10 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       mbar_init(&bars->k_empty[i], 1);
       mbar_init(&bars->v_full[i], 1);
       mbar_init(&bars->v_empty[i], 1);
-      mbar_init(&bars->s_full[i], 1);
       mbar_init(&bars->p_full[i], 128);
       mbar_init(&bars->p_empty[i], 1);
     }
+    for (int i = 0; i < 3; ++i) mbar_init(&bars->s_full[i], 1);
     mbar_init(&bars->o_full, 1);
     fence_barrier_init();
   }
@@ -158,14 +159,15 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
           const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
           const uint64_t ad = desc_kmajor<SW>(q_addr + bx * Cfg::BOX_BYTES, off);
           const uint64_t bd = desc_kmajor<SW>(k_addr + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, off);
-          mma_ss(tmem + Cfg::TMEM_S + st * 128, ad, bd, idesc_qk, ks > 0);
+          mma_ss(tmem + Cfg::TMEM_S + (i % 3) * 128, ad, bd, idesc_qk, ks > 0);
         }
         mma_commit(&bars->k_empty[st]);
-        mma_commit(&bars->s_full[st]);
+        mma_commit(&bars->s_full[i % 3]);
       };
       mbar_wait(&bars->q_full, 0);
       issue_qk(0);
       if (T > 1) issue_qk(1);
+      if (T > 2) issue_qk(2);
       for (int i = 0; i < T; ++i) {
         const int st = i & 1;
         mbar_wait(&bars->p_full[st], (i >> 1) & 1);
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
         }
         mma_commit(&bars->v_empty[st]);
         mma_commit(&bars->p_empty[st]);
-        if (i + 2 < T) issue_qk(i + 2);
+        if (i + 3 < T) issue_qk(i + 3);  // S ring slot i % 3 was released by p_full(i)
       }
       mma_commit(&bars->o_full);
     }
@@ -196,9 +198,9 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
     const int lim_i = msk.has_tgt ? min(i_pos, msk.max_id) : i_pos;
     const int full_lim = fast ? min(m0, msk.has_tgt ? msk.max_id : 0x7fffffff) : -1;
     uint8_t* sPw = sP + wg * Cfg::P_BYTES;
-    const uint32_t s_taddr = tmem + Cfg::TMEM_S + wg * 128 + lane_bits;
     for (int i = wg, it = 0; i < T; i += 2, ++it) {
-      mbar_wait(&bars->s_full[wg], it & 1);
+      const uint32_t s_taddr = tmem + Cfg::TMEM_S + (i % 3) * 128 + lane_bits;
+      mbar_wait(&bars->s_full[i % 3], (i / 3) & 1);
       tc_fence_after_sync();
       if (it >= 1) mbar_wait(&bars->p_empty[wg], (it - 1) & 1);
       const int n0 = (t0 + i) * 128;

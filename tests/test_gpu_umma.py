@@ -60,7 +60,8 @@ def test_umma_matches_generic_at_full_size(d, lmax, B, H):
         hstu_mha(lmax, alpha, qq, kk, vv, off, num_targets=nt, kernel=HammerKernel.CUDA, impl=impl).backward(do)
         grads[impl] = (qq.grad, kk.grad, vv.grad)
     for name, a, r in zip(("dq", "dk", "dv"), grads[_lib.IMPL_AUTO], grads[_lib.IMPL_GENERIC]):
-        assert_rel(a, r.float(), f"bwd umma vs generic {name} d={d} lmax={lmax}", tol=2e-3, operand_roundings=2)
+        # both sides are bf16 (1.7e-3 storage rounding each) and the tcgen05 side rounds P / dS to bf16 once more
+        assert_rel(a, r.float(), f"bwd umma vs generic {name} d={d} lmax={lmax}", tol=3.5e-3)
 
 
 def test_linearity_in_v_and_sequence_permutation():
