@@ -55,8 +55,8 @@ struct BwdCfg {
   static constexpr int OFF_Q = OFF_V + TILE_BYTES;        // 2 stages
   static constexpr int OFF_DO = OFF_Q + 2 * TILE_BYTES;   // 2 stages
   static constexpr int OFF_PT = OFF_DO + 2 * TILE_BYTES;
-  static constexpr int OFF_DST = OFF_PT + PT_BYTES;
-  static constexpr int OFF_BAR = OFF_DST + PT_BYTES;
+  static constexpr int OFF_DST = OFF_PT + 2 * PT_BYTES;   // P^T and dS^T are double-buffered (tile i -> buffer i & 1)
+  static constexpr int OFF_BAR = OFF_DST + 2 * PT_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int TMEM_ST = 0;          // S^T   [0,128)
   static constexpr int TMEM_DPT = 128;       // dP^T  [128,256)
@@ -69,7 +69,7 @@ struct BwdCfg {
 struct BwdBars {
   uint64_t kv_full;
   uint64_t q_full[2], q_empty[2];
-  uint64_t s_full, pds_full, pds_empty, dq_full, dq_empty, fin_full;
+  uint64_t s_full, pds_full, pds_empty[2], dq_full, dq_empty, fin_full;
   uint32_t tmem_base;
 };
 
@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     }
     mbar_init(&bars->s_full, 1);
     mbar_init(&bars->pds_full, 256);
-    mbar_init(&bars->pds_empty, 1);
+    mbar_init(&bars->pds_empty[0], 1);
+    mbar_init(&bars->pds_empty[1], 1);
     mbar_init(&bars->dq_full, 1);
     mbar_init(&bars->dq_empty, 256);
     mbar_init(&bars->fin_full, 1);
@@ -194,24 +195,24 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // K = 128 query rows
-          const uint64_t a_pt = desc_kmajor<128>(pt_addr + (ks >> 2) * 16384, (ks & 3) * 32);
+          const uint64_t a_pt = desc_kmajor<128>(pt_addr + st * Cfg::PT_BYTES + (ks >> 2) * 16384, (ks & 3) * 32);
           const uint64_t b_do = desc_mnmajor<SW>(do_addr + st * Cfg::TILE_BYTES, ks * 16, Cfg::BOX_BYTES);
           mma_ss(tmem + Cfg::TMEM_DV, a_pt, b_do, idesc_kv, (i > 0) || (ks > 0));
         }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a_ds = desc_kmajor<128>(dst_addr + (ks >> 2) * 16384, (ks & 3) * 32);
+          const uint64_t a_ds = desc_kmajor<128>(dst_addr + st * Cfg::PT_BYTES + (ks >> 2) * 16384, (ks & 3) * 32);
           const uint64_t b_q = desc_mnmajor<SW>(q_addr + st * Cfg::TILE_BYTES, ks * 16, Cfg::BOX_BYTES);
           mma_ss(tmem + Cfg::TMEM_DK, a_ds, b_q, idesc_kv, (i > 0) || (ks > 0));
         }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // K = 128 key rows
-          const uint64_t a_ds = desc_mnmajor<128>(dst_addr, ks * 16, 16384);
+          const uint64_t a_ds = desc_mnmajor<128>(dst_addr + st * Cfg::PT_BYTES, ks * 16, 16384);
           const uint64_t b_k = desc_mnmajor<SW>(k_addr, ks * 16, Cfg::BOX_BYTES);
           mma_ss(tmem + Cfg::TMEM_DQ, a_ds, b_k, idesc_dq, ks > 0);
         }
         mma_commit(&bars->q_empty[st]);
-        mma_commit(&bars->pds_empty);
+        mma_commit(&bars->pds_empty[st]);
         mma_commit(&bars->dq_full);
       }
       mma_commit(&bars->fin_full);
@@ -227,8 +228,6 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     const bool fast = msk.fast != 0;
     const bool j_ok = j_pos < len;
     const bool j_hist = j_ok && (!msk.has_tgt || j_pos < msk.max_id);  // fast mask: valid = (j_hist & i > j) | (i == j)
-    uint8_t* sPTw = sPT + wg * 16384;
-    uint8_t* sDSTw = sDST + wg * 16384;
     const int cbase = wg * 64;
     const int qcol0 = wg * (D / 2);                // dQ columns drained by this warpgroup
 
@@ -261,6 +260,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       // tile-uniform classification
       const bool full = fast && (m0 >= n0 + 128) && (m0 + 128 <= len) && (!msk.has_tgt || n0 + 128 <= msk.max_id);
       const int mode = full ? 0 : (fast ? 1 : 2);
+      const uint32_t sPTw = smem_u32(sPT + (i & 1) * Cfg::PT_BYTES + wg * 16384);
+      const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + wg * 16384);
       const int jr = j_pos - m0 - cbase;           // query column (relative to this warpgroup's block) equal to j
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
       const uint32_t st_addr = tmem + Cfg::TMEM_ST + cbase + lane_bits;
@@ -324,12 +325,12 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
           }
         }
 #undef HSTU_BWD_ELEM
-        if (c == 0 && i >= 1) mbar_wait(&bars->pds_empty, (i - 1) & 1);  // previous tile's GEMMs are done with P^T/dS^T
+        if (c == 0 && i >= 2) mbar_wait(&bars->pds_empty[i & 1], ((i >> 1) - 1) & 1);  // GEMMs of tile i-2 are done with this buffer
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const uint32_t off = swizzled_chunk_offset<128>(row, c * 4 + j4);
-          *reinterpret_cast<uint4*>(sPTw + off) = make_uint4(pp[4 * j4], pp[4 * j4 + 1], pp[4 * j4 + 2], pp[4 * j4 + 3]);
-          *reinterpret_cast<uint4*>(sDSTw + off) = make_uint4(dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
+          st_shared_v4(sPTw + off, pp[4 * j4], pp[4 * j4 + 1], pp[4 * j4 + 2], pp[4 * j4 + 3]);
+          st_shared_v4(sDSTw + off, dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
         }
       }
       tc_fence_before_sync();

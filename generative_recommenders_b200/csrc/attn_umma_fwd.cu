@@ -49,7 +49,8 @@ struct FwdCfg {
   static constexpr int OFF_K = OFF_Q + TILE_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * TILE_BYTES;
   static constexpr int OFF_P = OFF_V + STAGES * TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int NPB = (D <= 64) ? 2 : 1;             // P buffers per silu warpgroup
+  static constexpr int OFF_BAR = OFF_P + 2 * NPB * P_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
   static constexpr int TMEM_S = 0;      // ring of 3 S buffers: columns [0,128), [128,256), [256,384)
   static constexpr int TMEM_O = 384;    // O accumulator: columns [384, 384 + D)
@@ -59,7 +60,7 @@ struct FwdCfg {
 struct FwdBars {
   uint64_t q_full;
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
-  uint64_t s_full[3], p_full[2], p_empty[2];
+  uint64_t s_full[3], p_full[4], p_empty[4];
   uint64_t o_full;
   uint32_t tmem_base;
 };
@@ -98,6 +99,8 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       mbar_init(&bars->k_empty[i], 1);
       mbar_init(&bars->v_full[i], 1);
       mbar_init(&bars->v_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->p_full[i], 128);
       mbar_init(&bars->p_empty[i], 1);
     }
@@ -170,17 +173,18 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       if (T > 2) issue_qk(2);
       for (int i = 0; i < T; ++i) {
         const int st = i & 1;
-        mbar_wait(&bars->p_full[st], (i >> 1) & 1);
+        const int it = i >> 1, pbuf = st * Cfg::NPB + (it % Cfg::NPB);  // P buffer of tile i (owned by warpgroup i & 1)
+        mbar_wait(&bars->p_full[pbuf], (it / Cfg::NPB) & 1);
         mbar_wait(&bars->v_full[st], (i >> 1) & 1);
         tc_fence_after_sync();
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t ad = desc_kmajor<128>(p_addr + st * Cfg::P_BYTES + (ks >> 2) * 16384, (ks & 3) * 32);
+          const uint64_t ad = desc_kmajor<128>(p_addr + pbuf * Cfg::P_BYTES + (ks >> 2) * 16384, (ks & 3) * 32);
           const uint64_t bd = desc_mnmajor<SW>(v_addr + st * Cfg::TILE_BYTES, ks * 16, Cfg::BOX_BYTES);
           mma_ss(tmem + Cfg::TMEM_O, ad, bd, idesc_pv, (i > 0) || (ks > 0));
         }
         mma_commit(&bars->v_empty[st]);
-        mma_commit(&bars->p_empty[st]);
+        mma_commit(&bars->p_empty[pbuf]);
         if (i + 3 < T) issue_qk(i + 3);  // S ring slot i % 3 was released by p_full(i)
       }
       mma_commit(&bars->o_full);
@@ -197,12 +201,12 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
     // plain causal (+targets): valid(i, j) = (j < lim_i) | (j == i)   (common.cuh: mask_valid, fast path)
     const int lim_i = msk.has_tgt ? min(i_pos, msk.max_id) : i_pos;
     const int full_lim = fast ? min(m0, msk.has_tgt ? msk.max_id : 0x7fffffff) : -1;
-    uint8_t* sPw = sP + wg * Cfg::P_BYTES;
     for (int i = wg, it = 0; i < T; i += 2, ++it) {
       const uint32_t s_taddr = tmem + Cfg::TMEM_S + (i % 3) * 128 + lane_bits;
       mbar_wait(&bars->s_full[i % 3], (i / 3) & 1);
       tc_fence_after_sync();
-      if (it >= 1) mbar_wait(&bars->p_empty[wg], (it - 1) & 1);
+      const int pbuf = wg * Cfg::NPB + (it % Cfg::NPB), use = it / Cfg::NPB;
+      const uint32_t sPw = smem_u32(sP + pbuf * Cfg::P_BYTES);
       const int n0 = (t0 + i) * 128;
       const int mode = (n0 + 128 <= full_lim) ? 0 : (fast ? 1 : 2);  // tile-uniform: no divergence
       const int lim_rel = lim_i - n0, diag_rel = i_pos - n0;
@@ -242,16 +246,17 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
             pk[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
           }
         }
+        if (c == 0 && use >= 1) mbar_wait(&bars->p_empty[pbuf], (use - 1) & 1);  // the GEMM that last read this buffer is done
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const int cc = c * 4 + j4;  // 16-byte chunk index along the key dimension (0..15)
-          uint4 v = make_uint4(pk[4 * j4], pk[4 * j4 + 1], pk[4 * j4 + 2], pk[4 * j4 + 3]);
-          *reinterpret_cast<uint4*>(sPw + (cc >> 3) * 16384 + swizzled_chunk_offset<128>(row, cc & 7)) = v;
+          st_shared_v4(sPw + (cc >> 3) * 16384 + swizzled_chunk_offset<128>(row, cc & 7), pk[4 * j4], pk[4 * j4 + 1],
+                       pk[4 * j4 + 2], pk[4 * j4 + 3]);
         }
       }
       tc_fence_before_sync();
       fence_proxy_async_smem();
-      mbar_arrive(&bars->p_full[wg]);
+      mbar_arrive(&bars->p_full[pbuf]);
     }
     // ---------------- epilogue: O (TMEM) -> * 1/N -> global ----------------
     mbar_wait(&bars->o_full, 0);
