@@ -169,34 +169,10 @@ def run_ours(args):
         x_host = x_dev.cpu().pin_memory()
         off_host, nt_host, len_host = off.cpu().pin_memory(), nt.cpu().pin_memory(), lengths.cpu().pin_memory()
         h2d_bytes = x_host.numel() * 2 + off_host.numel() * 8 + nt_host.numel() * 4 + len_host.numel() * 4
-        comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-        pending = []
+        from generative_recommenders_b200.distributed import LayerBucketAllReduce
 
-        if world > 1:  # one flat all-reduce per STU layer, launched as soon as that layer's grads are final
-            for layer in stack._stu_layers:
-                lp = list(layer.parameters())
-                state = {"left": len(lp)}
-
-                def hook(_p, lp=lp, state=state):
-                    state["left"] -= 1
-                    if state["left"] == 0:
-                        state["left"] = len(lp)
-                        ready = torch.cuda.Event()
-                        ready.record(torch.cuda.current_stream(dev))
-                        with torch.cuda.stream(comm_stream):
-                            comm_stream.wait_event(ready)
-                            flat = torch.cat([q.grad.reshape(-1) for q in lp]).float()
-                            dist.all_reduce(flat)
-                            flat.div_(world)
-                            o = 0
-                            for q in lp:
-                                n = q.numel()
-                                q.grad.copy_(flat[o:o + n].view_as(q.grad))
-                                o += n
-                        pending.append(flat)
-
-                for q in lp:
-                    q.register_post_accumulate_grad_hook(hook)
+        # one flat NCCL all-reduce per STU layer, launched as soon as that layer's grads are final (side stream)
+        reducer = LayerBucketAllReduce(list(stack._stu_layers), world, dev) if world > 1 else None
 
         def step(e2e: bool):
             if e2e:
@@ -210,9 +186,8 @@ def run_ours(args):
             y = stack(x=x, x_lengths=l_, x_offsets=o_, max_seq_len=args.lmax, num_targets=n_)
             loss = y.float().square().mean()
             loss.backward()
-            if world > 1:
-                torch.cuda.current_stream(dev).wait_stream(comm_stream)
-                pending.clear()
+            if reducer is not None:
+                reducer.wait()
             opt.step()
             if e2e:
                 return float(loss.item())  # device -> host read of the step result

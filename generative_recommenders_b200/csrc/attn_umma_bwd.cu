@@ -52,9 +52,10 @@ struct BwdCfg {
   static constexpr int PT_BYTES = 128 * 128 * 2;
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + TILE_BYTES;
-  static constexpr int OFF_Q = OFF_V + TILE_BYTES;        // 2 stages
-  static constexpr int OFF_DO = OFF_Q + 2 * TILE_BYTES;   // 2 stages
-  static constexpr int OFF_PT = OFF_DO + 2 * TILE_BYTES;
+  static constexpr int STAGES = (D <= 32) ? 4 : 2;        // Q_i / dO_i TMA ring depth
+  static constexpr int OFF_Q = OFF_V + TILE_BYTES;
+  static constexpr int OFF_DO = OFF_Q + STAGES * TILE_BYTES;
+  static constexpr int OFF_PT = OFF_DO + STAGES * TILE_BYTES;
   static constexpr int OFF_DST = OFF_PT + 2 * PT_BYTES;   // P^T and dS^T are double-buffered (tile i -> buffer i & 1)
   static constexpr int OFF_BAR = OFF_DST + 2 * PT_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
@@ -68,7 +69,7 @@ struct BwdCfg {
 
 struct BwdBars {
   uint64_t kv_full;
-  uint64_t q_full[2], q_empty[2];
+  uint64_t q_full[4], q_empty[4];
   uint64_t s_full, pds_full, pds_empty[2], dq_full, dq_empty, fin_full;
   uint32_t tmem_base;
 };
@@ -81,6 +82,7 @@ template <int D, bool BF16>
 __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = BwdCfg<D>;
   constexpr int SW = Cfg::SW;
+  constexpr int NST = Cfg::STAGES;
   const int b = blockIdx.z, h = blockIdx.y;
   const int n0 = (int)blockIdx.x * 128;
   const long long row0 = load_index(p.seq_offsets, p.offsets_i64, b);
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     mbar_init(&bars->kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->q_full[i], 1);
       mbar_init(&bars->q_empty[i], 1);
     }
@@ -145,8 +147,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         tma_load_3d(sV + bx * Cfg::BOX_BYTES, &p.tmV, &bars->kv_full, bx * Cfg::BOX_COLS, h, (int)(row0 + n0));
       }
       for (int i = 0; i < T; ++i) {
-        const int st = i & 1;
-        if (i >= 2) mbar_wait(&bars->q_empty[st], ((i >> 1) - 1) & 1);
+        const int st = i % NST;
+        if (i >= NST) mbar_wait(&bars->q_empty[st], ((i / NST) - 1) & 1);
         mbar_arrive_expect_tx(&bars->q_full[st], 2 * Cfg::TILE_BYTES);
         const int qrow = (int)(row0 + (long long)q_tile(i) * 128);
 #pragma unroll
@@ -165,8 +167,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
       const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
       auto issue_s = [&](int i) {
-        const int st = i & 1;
-        mbar_wait(&bars->q_full[st], (i >> 1) & 1);
+        const int st = i % NST;
+        mbar_wait(&bars->q_full[st], (i / NST) & 1);
         tc_fence_after_sync();
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
@@ -185,7 +187,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       mbar_wait(&bars->kv_full, 0);
       issue_s(0);
       for (int i = 0; i < T; ++i) {
-        const int st = i & 1;
+        const int st = i % NST;   // Q / dO stage
+        const int pb = i & 1;     // P^T / dS^T buffer
         mbar_wait(&bars->pds_full, i & 1);  // P^T, dS^T of tile i are in smem; S^T / dP^T have been read
         tc_fence_after_sync();
         if (i + 1 < T) issue_s(i + 1);      // next tile's scores first: the warpgroups can start on them
@@ -195,24 +198,24 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // K = 128 query rows
-          const uint64_t a_pt = desc_kmajor<128>(pt_addr + st * Cfg::PT_BYTES + (ks >> 2) * 16384, (ks & 3) * 32);
+          const uint64_t a_pt = desc_kmajor<128>(pt_addr + pb * Cfg::PT_BYTES + (ks >> 2) * 16384, (ks & 3) * 32);
           const uint64_t b_do = desc_mnmajor<SW>(do_addr + st * Cfg::TILE_BYTES, ks * 16, Cfg::BOX_BYTES);
           mma_ss(tmem + Cfg::TMEM_DV, a_pt, b_do, idesc_kv, (i > 0) || (ks > 0));
         }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a_ds = desc_kmajor<128>(dst_addr + st * Cfg::PT_BYTES + (ks >> 2) * 16384, (ks & 3) * 32);
+          const uint64_t a_ds = desc_kmajor<128>(dst_addr + pb * Cfg::PT_BYTES + (ks >> 2) * 16384, (ks & 3) * 32);
           const uint64_t b_q = desc_mnmajor<SW>(q_addr + st * Cfg::TILE_BYTES, ks * 16, Cfg::BOX_BYTES);
           mma_ss(tmem + Cfg::TMEM_DK, a_ds, b_q, idesc_kv, (i > 0) || (ks > 0));
         }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // K = 128 key rows
-          const uint64_t a_ds = desc_mnmajor<128>(dst_addr + st * Cfg::PT_BYTES, ks * 16, 16384);
+          const uint64_t a_ds = desc_mnmajor<128>(dst_addr + pb * Cfg::PT_BYTES, ks * 16, 16384);
           const uint64_t b_k = desc_mnmajor<SW>(k_addr, ks * 16, Cfg::BOX_BYTES);
           mma_ss(tmem + Cfg::TMEM_DQ, a_ds, b_k, idesc_dq, ks > 0);
         }
         mma_commit(&bars->q_empty[st]);
-        mma_commit(&bars->pds_empty[st]);
+        mma_commit(&bars->pds_empty[pb]);
         mma_commit(&bars->dq_full);
       }
       mma_commit(&bars->fin_full);

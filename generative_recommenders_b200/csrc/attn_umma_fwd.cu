@@ -44,7 +44,7 @@ struct FwdCfg {
   static constexpr int BOX_BYTES = 128 * SW;
   static constexpr int TILE_BYTES = 128 * D * 2;
   static constexpr int P_BYTES = 128 * 128 * 2;
-  static constexpr int STAGES = 2;
+  static constexpr int STAGES = (D <= 32) ? 4 : 2;           // K / V TMA ring depth
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + TILE_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * TILE_BYTES;
@@ -59,7 +59,7 @@ struct FwdCfg {
 
 struct FwdBars {
   uint64_t q_full;
-  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
+  uint64_t k_full[4], k_empty[4], v_full[4], v_empty[4];
   uint64_t s_full[3], p_full[4], p_empty[4];
   uint64_t o_full;
   uint32_t tmem_base;
@@ -69,6 +69,7 @@ template <int D, bool BF16>
 __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_constant__ FwdParams p) {
   using Cfg = FwdCfg<D>;
   constexpr int SW = Cfg::SW;
+  constexpr int NST = Cfg::STAGES;
   const int b = blockIdx.z, h = blockIdx.y;
   const int m0 = (int)(gridDim.x - 1 - blockIdx.x) * 128;
   const long long row0 = load_index(p.seq_offsets, p.offsets_i64, b);
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     mbar_init(&bars->q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->k_full[i], 1);
       mbar_init(&bars->k_empty[i], 1);
       mbar_init(&bars->v_full[i], 1);
@@ -124,8 +125,8 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       for (int bx = 0; bx < Cfg::NBOX; ++bx)
         tma_load_3d(sQ + bx * Cfg::BOX_BYTES, &p.tmQ, &bars->q_full, bx * Cfg::BOX_COLS, h, (int)(row0 + m0));
       for (int i = 0; i < T; ++i) {
-        const int st = i & 1;
-        if (i >= 2) mbar_wait(&bars->k_empty[st], ((i >> 1) - 1) & 1);
+        const int st = i % NST;
+        if (i >= NST) mbar_wait(&bars->k_empty[st], ((i / NST) - 1) & 1);
         mbar_arrive_expect_tx(&bars->k_full[st], Cfg::TILE_BYTES);
 #pragma unroll
         for (int bx = 0; bx < Cfg::NBOX; ++bx)
@@ -138,8 +139,8 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       // ---------------- TMA producer: V tiles ----------------
       prefetch_tensormap(&p.tmV);
       for (int i = 0; i < T; ++i) {
-        const int st = i & 1;
-        if (i >= 2) mbar_wait(&bars->v_empty[st], ((i >> 1) - 1) & 1);
+        const int st = i % NST;
+        if (i >= NST) mbar_wait(&bars->v_empty[st], ((i / NST) - 1) & 1);
         mbar_arrive_expect_tx(&bars->v_full[st], Cfg::TILE_BYTES);
 #pragma unroll
         for (int bx = 0; bx < Cfg::NBOX; ++bx)
@@ -154,8 +155,8 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, BF16, BF16);
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
       auto issue_qk = [&](int i) {
-        const int st = i & 1;
-        mbar_wait(&bars->k_full[st], (i >> 1) & 1);
+        const int st = i % NST;
+        mbar_wait(&bars->k_full[st], (i / NST) & 1);
         tc_fence_after_sync();
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
@@ -172,10 +173,10 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       if (T > 1) issue_qk(1);
       if (T > 2) issue_qk(2);
       for (int i = 0; i < T; ++i) {
-        const int st = i & 1;
-        const int it = i >> 1, pbuf = st * Cfg::NPB + (it % Cfg::NPB);  // P buffer of tile i (owned by warpgroup i & 1)
+        const int st = i % NST;
+        const int it = i >> 1, pbuf = (i & 1) * Cfg::NPB + (it % Cfg::NPB);  // P buffer of tile i (owned by warpgroup i & 1)
         mbar_wait(&bars->p_full[pbuf], (it / Cfg::NPB) & 1);
-        mbar_wait(&bars->v_full[st], (i >> 1) & 1);
+        mbar_wait(&bars->v_full[st], (i / NST) & 1);
         tc_fence_after_sync();
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
