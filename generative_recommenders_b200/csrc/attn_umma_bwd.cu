@@ -2,16 +2,18 @@
 //
 // One CTA per (128-row KEY tile, head, sequence); early key tiles (the heavy ones under a causal mask) are scheduled
 // first.  K and V of the tile stay in shared memory; the CTA streams the query tiles that can attend to it
-// (Q_i and dO_i, 2-stage TMA ring) and per query tile issues five tcgen05 GEMMs (accumulators in TMEM):
-//     S^T  = K Q_i^T          (A = K  K-major,  B = Q_i  K-major)      [kv x q]
-//     dP^T = V dO_i^T         (A = V  K-major,  B = dO_i K-major)      [kv x q]
-//   -- two warpgroups (one key row per thread, 64 query columns each) turn S^T, dP^T into
+// (Q_i and dO_i, TMA ring of 2-4 stages).  Work is pipelined in half-tiles ("units": 128 key rows x 64 query rows):
+//     S^T  = K Q^T            (A = K  K-major,  B = 64 rows of Q_i  K-major)   -> TMEM slot, columns [0, 64)
+//     dP^T = V dO^T           (A = V  K-major,  B = 64 rows of dO_i K-major)   -> TMEM slot, columns [64, 128)
+//   The slots form a ring of 3 (2 for d = 64): the scores of unit u+3 are issued as soon as unit u has been read, so
+//   the two elementwise warpgroups (warpgroup h owns half h of every query tile; one key row per thread) always find
+//   their next scores ready.  They turn S^T, dP^T into
 //        P^T  = silu(alpha S)            * mask      (1/N folded into the dV epilogue)
 //        dS^T = dP sig (1 + x (1 - sig)) * mask      (alpha/N folded into the dK epilogue / dQ convert)
-//      as bf16 tiles in shared memory ([kv][q], q contiguous, 128B swizzle) --
-//     dV  += P^T  dO_i        (A = P^T  K-major,  B = dO_i MN-major)    [kv x d]   accumulates over all query tiles
-//     dK  += dS^T Q_i         (A = dS^T K-major,  B = Q_i  MN-major)    [kv x d]
-//     dQ_i = dS   K           (A = dS^T tile read MN-major, B = K MN-major)  [q x d]
+//   from ONE tanh per score and write them as bf16 boxes ([kv][q], q contiguous, 128B swizzle; two box pairs) --
+//     dV  += P^T  dO          (A = P^T box  K-major,  B = 64 rows of dO_i MN-major)   [kv x d]  all query tiles
+//     dK  += dS^T Q           (A = dS^T box K-major,  B = 64 rows of Q_i  MN-major)   [kv x d]
+//     dQ_i = dS   K           (A = both dS^T boxes of the tile read MN-major, B = K MN-major)   [128 q x d]
 //   dQ_i is added to an fp32 accumulator in global memory with 128-bit vector reductions (each key-tile CTA
 //   contributes to every later query tile); a small convert kernel scales it by alpha/N and writes bf16 dq.
 //
@@ -59,18 +61,20 @@ struct BwdCfg {
   static constexpr int OFF_DST = OFF_PT + 2 * PT_BYTES;   // P^T and dS^T are double-buffered (tile i -> buffer i & 1)
   static constexpr int OFF_BAR = OFF_DST + 2 * PT_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-  static constexpr int TMEM_ST = 0;          // S^T   [0,128)
-  static constexpr int TMEM_DPT = 128;       // dP^T  [128,256)
-  static constexpr int TMEM_DV = 256;        // dV    [256, 256+D)
-  static constexpr int TMEM_DK = 256 + D;    // dK
-  static constexpr int TMEM_DQ = 256 + 2 * D;  // dQ_i
-  static_assert(256 + 3 * D <= 512, "TMEM budget");
+  // TMEM: a ring of NSLOT score slots, each {S^T half-tile: 64 columns, dP^T half-tile: 64 columns} (a half-tile is
+  // 128 key rows x 64 query rows), followed by the dV, dK and dQ accumulators.
+  static constexpr int NSLOT = (384 + 3 * D <= 512) ? 3 : 2;
+  static constexpr int TMEM_SLOT = 0;
+  static constexpr int TMEM_DV = NSLOT * 128;
+  static constexpr int TMEM_DK = TMEM_DV + D;
+  static constexpr int TMEM_DQ = TMEM_DK + D;
+  static_assert(TMEM_DQ + D <= 512, "TMEM budget");
 };
 
 struct BwdBars {
   uint64_t kv_full;
   uint64_t q_full[4], q_empty[4];
-  uint64_t s_full, pds_full, pds_empty[2], dq_full, dq_empty, fin_full;
+  uint64_t s_full[3], unit_done[2], pair_empty[2], dq_full, dq_empty, fin_full;
   uint32_t tmem_base;
 };
 
@@ -118,10 +122,11 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       mbar_init(&bars->q_full[i], 1);
       mbar_init(&bars->q_empty[i], 1);
     }
-    mbar_init(&bars->s_full, 1);
-    mbar_init(&bars->pds_full, 256);
-    mbar_init(&bars->pds_empty[0], 1);
-    mbar_init(&bars->pds_empty[1], 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&bars->s_full[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->unit_done[i], 128);
+      mbar_init(&bars->pair_empty[i], 1);
+    }
     mbar_init(&bars->dq_full, 1);
     mbar_init(&bars->dq_empty, 256);
     mbar_init(&bars->fin_full, 1);
@@ -161,62 +166,72 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc_s = make_idesc(128, 128, false, false, BF16, BF16);   // S^T, dP^T
+      // Work is pipelined in "units" u = 2 i + h: half h (64 query rows) of query tile i.  Unit u's scores live in TMEM
+      // slot u % NSLOT; warpgroup h turns them into the P^T / dS^T box (pair i & 1, box h) in shared memory.
+      constexpr int NSLOT = Cfg::NSLOT;
+      constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, BF16, BF16);    // S^T, dP^T half-tiles
       constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dV, dK: A K-major, B MN-major
       constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // dQ: A MN-major, B MN-major
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
       const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
-      auto issue_s = [&](int i) {
-        const int st = i % NST;
-        mbar_wait(&bars->q_full[st], (i / NST) & 1);
-        tc_fence_after_sync();
-#pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
-          mma_ss(tmem + Cfg::TMEM_ST, desc_kmajor<SW>(k_addr + bx * Cfg::BOX_BYTES, off),
-                 desc_kmajor<SW>(q_addr + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, off), idesc_s, ks > 0);
-        }
-#pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
-          mma_ss(tmem + Cfg::TMEM_DPT, desc_kmajor<SW>(v_addr + bx * Cfg::BOX_BYTES, off),
-                 desc_kmajor<SW>(do_addr + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, off), idesc_s, ks > 0);
-        }
-        mma_commit(&bars->s_full);
-      };
-      mbar_wait(&bars->kv_full, 0);
-      issue_s(0);
-      for (int i = 0; i < T; ++i) {
-        const int st = i % NST;   // Q / dO stage
-        const int pb = i & 1;     // P^T / dS^T buffer
-        mbar_wait(&bars->pds_full, i & 1);  // P^T, dS^T of tile i are in smem; S^T / dP^T have been read
-        tc_fence_after_sync();
-        if (i + 1 < T) issue_s(i + 1);      // next tile's scores first: the warpgroups can start on them
-        if (i >= 1) {
-          mbar_wait(&bars->dq_empty, (i - 1) & 1);  // dQ_{i-1} has been drained from TMEM
+      const int U = 2 * T;
+      auto issue_s = [&](int u) {
+        const int i = u >> 1, hf = u & 1, st = i % NST, slot = u % NSLOT;
+        if (hf == 0) {
+          mbar_wait(&bars->q_full[st], (i / NST) & 1);
           tc_fence_after_sync();
         }
+        const uint32_t rows_off = hf * 64 * SW;  // query rows [64 hf, 64 hf + 64) of the staged Q_i / dO_i tiles
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // K = 128 query rows
-          const uint64_t a_pt = desc_kmajor<128>(pt_addr + pb * Cfg::PT_BYTES + (ks >> 2) * 16384, (ks & 3) * 32);
-          const uint64_t b_do = desc_mnmajor<SW>(do_addr + st * Cfg::TILE_BYTES, ks * 16, Cfg::BOX_BYTES);
-          mma_ss(tmem + Cfg::TMEM_DV, a_pt, b_do, idesc_kv, (i > 0) || (ks > 0));
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
+          mma_ss(tmem + Cfg::TMEM_SLOT + slot * 128, desc_kmajor<SW>(k_addr + bx * Cfg::BOX_BYTES, off),
+                 desc_kmajor<SW>(q_addr + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES + rows_off, off), idesc_s, ks > 0);
         }
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a_ds = desc_kmajor<128>(dst_addr + pb * Cfg::PT_BYTES + (ks >> 2) * 16384, (ks & 3) * 32);
-          const uint64_t b_q = desc_mnmajor<SW>(q_addr + st * Cfg::TILE_BYTES, ks * 16, Cfg::BOX_BYTES);
-          mma_ss(tmem + Cfg::TMEM_DK, a_ds, b_q, idesc_kv, (i > 0) || (ks > 0));
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
+          mma_ss(tmem + Cfg::TMEM_SLOT + slot * 128 + 64, desc_kmajor<SW>(v_addr + bx * Cfg::BOX_BYTES, off),
+                 desc_kmajor<SW>(do_addr + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES + rows_off, off), idesc_s, ks > 0);
+        }
+        mma_commit(&bars->s_full[slot]);
+      };
+      mbar_wait(&bars->kv_full, 0);
+      tc_fence_after_sync();
+      for (int u = 0; u < NSLOT && u < U; ++u) issue_s(u);
+      for (int u = 0; u < U; ++u) {
+        const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1;
+        mbar_wait(&bars->unit_done[hf], i & 1);  // box (pb, hf) of P^T / dS^T is written, slot u % NSLOT has been read
+        tc_fence_after_sync();
+        if (u + NSLOT < U) issue_s(u + NSLOT);   // refill the slot first: the other warpgroup is waiting for scores
+        const uint32_t box = pb * Cfg::PT_BYTES + hf * 16384;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {  // K = the 64 query rows of this half
+          const uint64_t a_pt = desc_kmajor<128>(pt_addr + box, ks * 32);
+          const uint64_t b_do = desc_mnmajor<SW>(do_addr + st * Cfg::TILE_BYTES, hf * 64 + ks * 16, Cfg::BOX_BYTES);
+          mma_ss(tmem + Cfg::TMEM_DV, a_pt, b_do, idesc_kv, (u > 0) || (ks > 0));
         }
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // K = 128 key rows
-          const uint64_t a_ds = desc_mnmajor<128>(dst_addr + pb * Cfg::PT_BYTES, ks * 16, 16384);
-          const uint64_t b_k = desc_mnmajor<SW>(k_addr, ks * 16, Cfg::BOX_BYTES);
-          mma_ss(tmem + Cfg::TMEM_DQ, a_ds, b_k, idesc_dq, ks > 0);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t a_ds = desc_kmajor<128>(dst_addr + box, ks * 32);
+          const uint64_t b_q = desc_mnmajor<SW>(q_addr + st * Cfg::TILE_BYTES, hf * 64 + ks * 16, Cfg::BOX_BYTES);
+          mma_ss(tmem + Cfg::TMEM_DK, a_ds, b_q, idesc_kv, (u > 0) || (ks > 0));
         }
-        mma_commit(&bars->q_empty[st]);
-        mma_commit(&bars->pds_empty[pb]);
-        mma_commit(&bars->dq_full);
+        if (hf == 1) {
+          if (i >= 1) {
+            mbar_wait(&bars->dq_empty, (i - 1) & 1);  // dQ_{i-1} has been drained from TMEM
+            tc_fence_after_sync();
+          }
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {  // K = 128 key rows; A = both boxes of the pair read MN-major (M = 128 query rows)
+            const uint64_t a_ds = desc_mnmajor<128>(dst_addr + pb * Cfg::PT_BYTES, ks * 16, 16384);
+            const uint64_t b_k = desc_mnmajor<SW>(k_addr, ks * 16, Cfg::BOX_BYTES);
+            mma_ss(tmem + Cfg::TMEM_DQ, a_ds, b_k, idesc_dq, ks > 0);
+          }
+          mma_commit(&bars->q_empty[st]);
+          mma_commit(&bars->pair_empty[pb]);
+          mma_commit(&bars->dq_full);
+        }
       }
       mma_commit(&bars->fin_full);
     }
@@ -257,18 +272,20 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     };
 
     for (int i = 0; i < T; ++i) {
+      const int u = 2 * i + wg, slot = u % Cfg::NSLOT;
       const int m0 = q_tile(i) * 128;
-      mbar_wait(&bars->s_full, i & 1);
+      mbar_wait(&bars->s_full[slot], (u / Cfg::NSLOT) & 1);
       tc_fence_after_sync();
-      // tile-uniform classification
-      const bool full = fast && (m0 >= n0 + 128) && (m0 + 128 <= len) && (!msk.has_tgt || n0 + 128 <= msk.max_id);
+      // classification of this half-tile (uniform over the warpgroup)
+      const int mh0 = m0 + cbase;                   // first query row of the half
+      const bool full = fast && (mh0 >= n0 + 128) && (mh0 + 64 <= len) && (!msk.has_tgt || n0 + 128 <= msk.max_id);
       const int mode = full ? 0 : (fast ? 1 : 2);
       const uint32_t sPTw = smem_u32(sPT + (i & 1) * Cfg::PT_BYTES + wg * 16384);
       const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + wg * 16384);
       const int jr = j_pos - m0 - cbase;           // query column (relative to this warpgroup's block) equal to j
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
-      const uint32_t st_addr = tmem + Cfg::TMEM_ST + cbase + lane_bits;
-      const uint32_t dp_addr = tmem + Cfg::TMEM_DPT + cbase + lane_bits;
+      const uint32_t st_addr = tmem + Cfg::TMEM_SLOT + slot * 128 + lane_bits;
+      const uint32_t dp_addr = st_addr + 64;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {  // 2 chunks of 32 query columns
         uint32_t s[32], dp[32];
@@ -328,7 +345,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
           }
         }
 #undef HSTU_BWD_ELEM
-        if (c == 0 && i >= 2) mbar_wait(&bars->pds_empty[i & 1], ((i >> 1) - 1) & 1);  // GEMMs of tile i-2 are done with this buffer
+        if (c == 0 && i >= 2) mbar_wait(&bars->pair_empty[i & 1], ((i >> 1) - 1) & 1);  // GEMMs of tile i-2 are done with this buffer pair
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const uint32_t off = swizzled_chunk_offset<128>(row, c * 4 + j4);
@@ -338,7 +355,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       }
       tc_fence_before_sync();
       fence_proxy_async_smem();
-      mbar_arrive(&bars->pds_full);
+      mbar_arrive(&bars->unit_done[wg]);
       if (i >= 1) drain_dq(i - 1);
     }
     drain_dq(T - 1);
