@@ -303,6 +303,7 @@ def run_ours(args):
             "bwd_hbm_gbs_algorithmic": abytes["bwd"] / (kt["attn_bwd"] * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
             "attn_share_of_step": (kt["attn_bwd"] + kt["attn_fwd"]) * per_step_calls / (ms / args.steps),
         }
+    out["kernel_ms_per_call"] = {k: round(v, 4) for k, v in sorted(kt.items())}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, seconds_budget=20.0)
     if world > 1:

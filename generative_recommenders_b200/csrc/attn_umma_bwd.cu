@@ -69,12 +69,15 @@ struct BwdCfg {
   static constexpr int TMEM_DK = TMEM_DV + D;
   static constexpr int TMEM_DQ = TMEM_DK + D;
   static_assert(TMEM_DQ + D <= 512, "TMEM budget");
+  // scripts/sim_bwd_protocol.py: a 3-slot score ring needs the Q/dO ring to be at least 4 deep (the scores of tile i+2 are
+  // requested before tile i releases its stage), otherwise the producer and the MMA issuer wait on each other.
+  static_assert(NSLOT == 2 || STAGES >= 4, "3-slot score ring needs >= 4 Q/dO stages");
 };
 
 struct BwdBars {
   uint64_t kv_full;
   uint64_t q_full[4], q_empty[4];
-  uint64_t s_full[3], unit_done[2], pair_empty[2], dq_full, dq_empty, fin_full;
+  uint64_t s_full[3], unit_done[4], pair_empty[2], dq_full, dq_empty, fin_full;
   uint32_t tmem_base;
 };
 
@@ -123,10 +126,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       mbar_init(&bars->q_empty[i], 1);
     }
     for (int i = 0; i < 3; ++i) mbar_init(&bars->s_full[i], 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->unit_done[i], 128);
-      mbar_init(&bars->pair_empty[i], 1);
-    }
+    for (int i = 0; i < 4; ++i) mbar_init(&bars->unit_done[i], 128);
+    for (int i = 0; i < 2; ++i) mbar_init(&bars->pair_empty[i], 1);
     mbar_init(&bars->dq_full, 1);
     mbar_init(&bars->dq_empty, 256);
     mbar_init(&bars->fin_full, 1);
@@ -201,7 +202,10 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       for (int u = 0; u < NSLOT && u < U; ++u) issue_s(u);
       for (int u = 0; u < U; ++u) {
         const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1;
-        mbar_wait(&bars->unit_done[hf], i & 1);  // box (pb, hf) of P^T / dS^T is written, slot u % NSLOT has been read
+        // box (pb, hf) of P^T / dS^T is written and slot u % NSLOT has been read.  One barrier per (half, tile parity): with a
+        // 3-slot score ring a warpgroup may finish TWO units before this thread gets here; a single barrier per half would
+        // then be two phases ahead and the parity wait would alias.
+        mbar_wait(&bars->unit_done[hf * 2 + pb], (i >> 1) & 1);
         tc_fence_after_sync();
         if (u + NSLOT < U) issue_s(u + NSLOT);   // refill the slot first: the other warpgroup is waiting for scores
         const uint32_t box = pb * Cfg::PT_BYTES + hf * 16384;
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       }
       tc_fence_before_sync();
       fence_proxy_async_smem();
-      mbar_arrive(&bars->unit_done[wg]);
+      mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);
       if (i >= 1) drain_dq(i - 1);
     }
     drain_dq(T - 1);

@@ -14,7 +14,7 @@ namespace hstu {
 constexpr int kNormThreads = 256;
 constexpr int kNormWarps = kNormThreads / 32;
 constexpr int kMaxPerLane = 32;     // 32 lanes * 32 = 1024 elements per normalised vector
-constexpr int kPartialRows = 592;   // 148 SMs * 4 CTAs
+constexpr int kPartialRows = 2368;  // 148 SMs * 16 CTAs: enough warps in flight to cover HBM latency
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -6,6 +6,7 @@
 #include <cuda.h>  // CUtensorMap (types only; the driver entry point is resolved at run time)
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace hstu {
 namespace umma {
@@ -57,12 +58,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifdef HSTU_DEBUG_SPIN
+// debug build: report the wait site that timed out (line number) instead of trapping, then fall through
+__device__ __forceinline__ void mbar_wait_line(uint64_t* bar, uint32_t parity, int line) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 20)) {
+      printf("MBAR TIMEOUT line %d block (%d,%d,%d) thread %d parity %u\n", line, (int)blockIdx.x, (int)blockIdx.y,
+             (int)blockIdx.z, (int)threadIdx.x, parity);
+      return;
+    }
+  }
+}
+#define mbar_wait(bar, parity) mbar_wait_line(bar, parity, __LINE__)
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > HSTU_SPIN_LIMIT) __trap();
   }
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // fences

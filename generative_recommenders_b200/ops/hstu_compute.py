@@ -25,7 +25,7 @@ def cuda_silu_fwd(x: torch.Tensor) -> torch.Tensor:
     dev = _lib.require_cuda(x)
     n, c = x.shape
     y = torch.empty((n, c), dtype=x.dtype, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _lib.timed("silu_fwd", dev):
         _lib.check(_lib.lib().hstu_silu_fwd(x.data_ptr(), y.data_ptr(), n, c, x.stride(0), y.stride(0), _lib.dtype_code(x),
                                             _lib.stream_ptr(dev)), "hstu_silu_fwd")
         _lib.note_launch(1)
@@ -36,7 +36,7 @@ def cuda_silu_bwd(dy: torch.Tensor, x: torch.Tensor, dx: torch.Tensor) -> None:
     dev = x.device
     n, c = x.shape
     dy = dy if dy.stride(-1) == 1 else dy.contiguous()
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _lib.timed("silu_bwd", dev):
         _lib.check(_lib.lib().hstu_silu_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), n, c, dy.stride(0), x.stride(0),
                                             dx.stride(0), _lib.dtype_code(x), _lib.stream_ptr(dev)), "hstu_silu_bwd")
         _lib.note_launch(1)
@@ -80,7 +80,7 @@ def cuda_norm_mul_dropout_fwd(attn, u, w, b, eps, p, seed, silu_u, concat_ux, gr
     nstat = n * (num_heads if group_norm else 1)
     mean = torch.empty(nstat, dtype=torch.float32, device=dev)
     rstd = torch.empty(nstat, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _lib.timed("nmd_fwd", dev):
         _lib.check(
             _lib.lib().hstu_norm_mul_dropout_fwd(attn.data_ptr(), u.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(),
                                                  mean.data_ptr(), rstd.data_ptr(), n, num_heads, linear_dim, attn.stride(0),
@@ -103,7 +103,7 @@ def cuda_norm_mul_dropout_bwd(dy, attn, u, w, b, mean, rstd, p, seed, silu_u, co
     db = torch.empty(np_, dtype=torch.float32, device=dev)
     part = _partial(np_, dev)
     dy = dy.contiguous()
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _lib.timed("nmd_bwd", dev):
         _lib.check(
             _lib.lib().hstu_norm_mul_dropout_bwd(dy.data_ptr(), attn.data_ptr(), u.data_ptr(), w.data_ptr(), b.data_ptr(),
                                                  mean.data_ptr(), rstd.data_ptr(), dattn.data_ptr(), du.data_ptr(),

@@ -29,7 +29,7 @@ def cuda_layer_norm_fwd(x2: torch.Tensor, weight, bias, eps: float, swish: bool,
     rstd = torch.empty(n, dtype=torch.float32, device=dev) if save_stats else None
     w = None if weight is None else weight.to(x2.dtype).contiguous()
     b = None if bias is None else bias.to(x2.dtype).contiguous()
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _lib.timed("ln_fwd", dev):
         _lib.check(
             _lib.lib().hstu_layer_norm_fwd(x2.data_ptr(), _lib.ptr(w), _lib.ptr(b), y.data_ptr(), _lib.ptr(mean),
                                            _lib.ptr(rstd), n, D, x2.stride(0), y.stride(0), eps, _lib.dtype_code(x2),
@@ -49,7 +49,7 @@ def cuda_layer_norm_bwd(dy2, x2, weight, bias, mean, rstd, swish: bool, need_wgr
     part = _partial(D, dev) if need_wgrad else None
     w = None if weight is None else weight.to(x2.dtype).contiguous()
     b = None if bias is None else bias.to(x2.dtype).contiguous()
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _lib.timed("ln_bwd", dev):
         _lib.check(
             _lib.lib().hstu_layer_norm_bwd(dy2.data_ptr(), x2.data_ptr(), _lib.ptr(w), _lib.ptr(b), mean.data_ptr(),
                                            rstd.data_ptr(), dx.data_ptr(), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(part), n,
