@@ -69,6 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     extra = ["-Xptxas", "-v"] if verbose else []
     if os.environ.get("HSTU_DEBUG_SPIN"):
         extra.append("-DHSTU_DEBUG_SPIN")
+    for flag in os.environ.get("HSTU_EXP", "").split():
+        extra.append("-D" + flag)
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile(s, extra), SOURCES))
     cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -165,80 +165,97 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      // Work is pipelined in "units" u = 2 i + h: half h (64 query rows) of query tile i.  Unit u's scores live in TMEM
-      // slot u % NSLOT; warpgroup h turns them into the P^T / dS^T box (pair i & 1, box h) in shared memory.
-      constexpr int NSLOT = Cfg::NSLOT;
-      constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, BF16, BF16);    // S^T, dP^T half-tiles
-      constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dV, dK: A K-major, B MN-major
-      constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // dQ: A MN-major, B MN-major
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
-      const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
-      const int U = 2 * T;
-      auto issue_s = [&](int u) {
-        const int i = u >> 1, hf = u & 1, st = i % NST, slot = u % NSLOT;
-        if (hf == 0) {
-          mbar_wait(&bars->q_full[st], (i / NST) & 1);
-          tc_fence_after_sync();
-        }
-        const uint32_t rows_off = hf * 64 * SW;  // query rows [64 hf, 64 hf + 64) of the staged Q_i / dO_i tiles
+    // ---------------- MMA issuer ----------------
+    // Work is pipelined in "units" u = 2 i + h: half h (64 query rows) of query tile i.  Unit u's scores live in TMEM
+    // slot u % NSLOT; warpgroup h turns them into the P^T / dS^T box (pair i & 1, box h) in shared memory.
+    // The whole warp runs the warp-uniform control flow, one fixed lane issues; descriptors are built once and only
+    // their address field is advanced (the issuing thread is on the critical path: ~32 MMAs per query tile).
+    constexpr int NSLOT = Cfg::NSLOT;
+    const bool leader = lane == 0;
+    constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, BF16, BF16);    // S^T, dP^T half-tiles
+    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dV, dK: A K-major, B MN-major
+    constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // dQ: A MN-major, B MN-major
+    const uint64_t dk_k = desc_kmajor<SW>(smem_u32(sK), 0);                        // K as K-major A (S^T)
+    const uint64_t dv_k = desc_kmajor<SW>(smem_u32(sV), 0);                        // V as K-major A (dP^T)
+    const uint64_t dq_k = desc_kmajor<SW>(smem_u32(sQ), 0);                        // Q_i rows as K-major B
+    const uint64_t ddo_k = desc_kmajor<SW>(smem_u32(sDO), 0);                      // dO_i rows as K-major B
+    const uint64_t dpt_k = desc_kmajor<128>(smem_u32(sPT), 0);                     // P^T box as K-major A
+    const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box as K-major A
+    const uint64_t dds_mn = desc_mnmajor<128>(smem_u32(sDST), 0, 16384);           // dS^T pair as MN-major A (dQ)
+    const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
+    const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
+    const uint64_t dk_mn = desc_mnmajor<SW>(smem_u32(sK), 0, Cfg::BOX_BYTES);      // K as MN-major B (dQ)
+    const int U = 2 * T;
+    auto issue_s = [&](int u) {
+      const int i = u >> 1, hf = u & 1, st = i % NST, slot = u % NSLOT;
+      if (hf == 0) {
+        mbar_wait(&bars->q_full[st], (i / NST) & 1);
+        tc_fence_after_sync();
+      }
+      // query rows [64 hf, 64 hf + 64) of the staged Q_i / dO_i tiles
+      const uint64_t row_off = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);
+      const uint32_t ts = tmem + Cfg::TMEM_SLOT + slot * 128;
+      if (leader) {
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
           const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
-          mma_ss(tmem + Cfg::TMEM_SLOT + slot * 128, desc_kmajor<SW>(k_addr + bx * Cfg::BOX_BYTES, off),
-                 desc_kmajor<SW>(q_addr + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES + rows_off, off), idesc_s, ks > 0);
+          const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
+          mma_ss(ts, dk_k + o, dq_k + row_off + o, idesc_s, ks > 0);
         }
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
           const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
-          mma_ss(tmem + Cfg::TMEM_SLOT + slot * 128 + 64, desc_kmajor<SW>(v_addr + bx * Cfg::BOX_BYTES, off),
-                 desc_kmajor<SW>(do_addr + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES + rows_off, off), idesc_s, ks > 0);
+          const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
+          mma_ss(ts + 64, dv_k + o, ddo_k + row_off + o, idesc_s, ks > 0);
         }
         mma_commit(&bars->s_full[slot]);
-      };
-      mbar_wait(&bars->kv_full, 0);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&bars->kv_full, 0);
+    tc_fence_after_sync();
+    for (int u = 0; u < NSLOT && u < U; ++u) issue_s(u);
+    for (int u = 0; u < U; ++u) {
+      const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1;
+      // box (pb, hf) of P^T / dS^T is written and slot u % NSLOT has been read.  One barrier per (half, tile parity): with a
+      // 3-slot score ring a warpgroup may finish TWO units before this thread gets here; a single barrier per half would
+      // then be two phases ahead and the parity wait would alias.
+      mbar_wait(&bars->unit_done[hf * 2 + pb], (i >> 1) & 1);
       tc_fence_after_sync();
-      for (int u = 0; u < NSLOT && u < U; ++u) issue_s(u);
-      for (int u = 0; u < U; ++u) {
-        const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1;
-        // box (pb, hf) of P^T / dS^T is written and slot u % NSLOT has been read.  One barrier per (half, tile parity): with a
-        // 3-slot score ring a warpgroup may finish TWO units before this thread gets here; a single barrier per half would
-        // then be two phases ahead and the parity wait would alias.
-        mbar_wait(&bars->unit_done[hf * 2 + pb], (i >> 1) & 1);
-        tc_fence_after_sync();
-        if (u + NSLOT < U) issue_s(u + NSLOT);   // refill the slot first: the other warpgroup is waiting for scores
-        const uint32_t box = pb * Cfg::PT_BYTES + hf * 16384;
+      if (u + NSLOT < U) issue_s(u + NSLOT);   // refill the slot first: the other warpgroup is waiting for scores
+      const uint64_t box = (uint64_t)((pb * Cfg::PT_BYTES + hf * 16384) >> 4);
+      const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);  // MN-major B: K rows = the 64 query rows
+      if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {  // K = the 64 query rows of this half
-          const uint64_t a_pt = desc_kmajor<128>(pt_addr + box, ks * 32);
-          const uint64_t b_do = desc_mnmajor<SW>(do_addr + st * Cfg::TILE_BYTES, hf * 64 + ks * 16, Cfg::BOX_BYTES);
-          mma_ss(tmem + Cfg::TMEM_DV, a_pt, b_do, idesc_kv, (u > 0) || (ks > 0));
+        for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
+          mma_ss(tmem + Cfg::TMEM_DV, dpt_k + box + (uint64_t)((ks * 32) >> 4), ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4),
+                 idesc_kv, (u > 0) || (ks > 0));
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          mma_ss(tmem + Cfg::TMEM_DK, dds_k + box + (uint64_t)((ks * 32) >> 4), dq_mn + rows + (uint64_t)((ks * 16 * SW) >> 4),
+                 idesc_kv, (u > 0) || (ks > 0));
+      }
+      __syncwarp();
+      if (hf == 1) {
+        if (i >= 1) {
+          mbar_wait(&bars->dq_empty, (i - 1) & 1);  // dQ_{i-1} has been drained from TMEM
+          tc_fence_after_sync();
         }
+        if (leader) {
+          const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t a_ds = desc_kmajor<128>(dst_addr + box, ks * 32);
-          const uint64_t b_q = desc_mnmajor<SW>(q_addr + st * Cfg::TILE_BYTES, hf * 64 + ks * 16, Cfg::BOX_BYTES);
-          mma_ss(tmem + Cfg::TMEM_DK, a_ds, b_q, idesc_kv, (u > 0) || (ks > 0));
-        }
-        if (hf == 1) {
-          if (i >= 1) {
-            mbar_wait(&bars->dq_empty, (i - 1) & 1);  // dQ_{i-1} has been drained from TMEM
-            tc_fence_after_sync();
-          }
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {  // K = 128 key rows; A = both boxes of the pair read MN-major (M = 128 query rows)
-            const uint64_t a_ds = desc_mnmajor<128>(dst_addr + pb * Cfg::PT_BYTES, ks * 16, 16384);
-            const uint64_t b_k = desc_mnmajor<SW>(k_addr, ks * 16, Cfg::BOX_BYTES);
-            mma_ss(tmem + Cfg::TMEM_DQ, a_ds, b_k, idesc_dq, ks > 0);
-          }
+          for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows; A = both boxes of the pair read MN-major (M = 128 query rows)
+            mma_ss(tmem + Cfg::TMEM_DQ, dds_mn + pair + (uint64_t)((ks * 16 * 128) >> 4), dk_mn + (uint64_t)((ks * 16 * SW) >> 4),
+                   idesc_dq, ks > 0);
           mma_commit(&bars->q_empty[st]);
           mma_commit(&bars->pair_empty[pb]);
           mma_commit(&bars->dq_full);
         }
+        __syncwarp();
       }
-      mma_commit(&bars->fin_full);
     }
+    if (leader) mma_commit(&bars->fin_full);
+    __syncwarp();
   } else if (warp >= 4) {
     // ---------------- elementwise warpgroups ----------------
     const int wg = (warp - 4) >> 2;                // owns query columns [64*wg, 64*wg + 64) of every tile
@@ -264,7 +281,11 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         uint32_t r[16];
         tmem_ld16(tmem + Cfg::TMEM_DQ + qcol0 + c * 16 + lane_bits, r);
         tmem_ld_wait();
+#ifdef HSTU_EXP_NO_DQ_RED
+        if (qpos < -1) {
+#else
         if (qpos < len) {
+#endif
 #pragma unroll
           for (int e = 0; e < 16; e += 4)
             red_add_v4(dst + c * 16 + e, __uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]),

@@ -149,47 +149,64 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc_qk = make_idesc(128, 128, false, false, BF16, BF16);
-      constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, BF16, BF16);
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
-      auto issue_qk = [&](int i) {
-        const int st = i % NST;
-        mbar_wait(&bars->k_full[st], (i / NST) & 1);
-        tc_fence_after_sync();
+    // ---------------- MMA issuer ----------------
+    // The whole warp runs the (warp-uniform) control flow and one fixed lane issues: descriptor arithmetic then stays in
+    // the uniform datapath.  Descriptors are built once; per MMA only the 14-bit address field moves (one 64-bit add of a
+    // compile-time constant): the single issuing thread is on the critical path of every tile.
+    const bool leader = lane == 0;
+    constexpr uint32_t idesc_qk = make_idesc(128, 128, false, false, BF16, BF16);
+    constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, BF16, BF16);
+    const uint64_t dq0 = desc_kmajor<SW>(smem_u32(sQ), 0);
+    const uint64_t dk0 = desc_kmajor<SW>(smem_u32(sK), 0);
+    const uint64_t dp0 = desc_kmajor<128>(smem_u32(sP), 0);
+    const uint64_t dv0 = desc_mnmajor<SW>(smem_u32(sV), 0, Cfg::BOX_BYTES);
+    auto issue_qk = [&](int i) {
+      const int st = i % NST;
+      mbar_wait(&bars->k_full[st], (i / NST) & 1);
+      tc_fence_after_sync();
+      const uint64_t kd = dk0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
+      const uint32_t ts = tmem + Cfg::TMEM_S + (i % 3) * 128;
+      if (leader) {
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
+          constexpr int dummy = 0;
           const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
-          const uint64_t ad = desc_kmajor<SW>(q_addr + bx * Cfg::BOX_BYTES, off);
-          const uint64_t bd = desc_kmajor<SW>(k_addr + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, off);
-          mma_ss(tmem + Cfg::TMEM_S + (i % 3) * 128, ad, bd, idesc_qk, ks > 0);
+          const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
+          mma_ss(ts, dq0 + o, kd + o, idesc_qk, ks > 0);
+          (void)dummy;
         }
         mma_commit(&bars->k_empty[st]);
         mma_commit(&bars->s_full[i % 3]);
-      };
-      mbar_wait(&bars->q_full, 0);
-      issue_qk(0);
-      if (T > 1) issue_qk(1);
-      if (T > 2) issue_qk(2);
-      for (int i = 0; i < T; ++i) {
-        const int st = i % NST;
-        const int it = i >> 1, pbuf = (i & 1) * Cfg::NPB + (it % Cfg::NPB);  // P buffer of tile i (owned by warpgroup i & 1)
-        mbar_wait(&bars->p_full[pbuf], (it / Cfg::NPB) & 1);
-        mbar_wait(&bars->v_full[st], (i / NST) & 1);
-        tc_fence_after_sync();
+      }
+      __syncwarp();
+    };
+    mbar_wait(&bars->q_full, 0);
+    issue_qk(0);
+    if (T > 1) issue_qk(1);
+    if (T > 2) issue_qk(2);
+    for (int i = 0; i < T; ++i) {
+      const int st = i % NST;
+      const int it = i >> 1, pbuf = (i & 1) * Cfg::NPB + (it % Cfg::NPB);  // P buffer of tile i (owned by warpgroup i & 1)
+      mbar_wait(&bars->p_full[pbuf], (it / Cfg::NPB) & 1);
+      mbar_wait(&bars->v_full[st], (i / NST) & 1);
+      tc_fence_after_sync();
+      const uint64_t pd = dp0 + (uint64_t)((pbuf * Cfg::P_BYTES) >> 4);
+      const uint64_t vd = dv0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
+      if (leader) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t ad = desc_kmajor<128>(p_addr + pbuf * Cfg::P_BYTES + (ks >> 2) * 16384, (ks & 3) * 32);
-          const uint64_t bd = desc_mnmajor<SW>(v_addr + st * Cfg::TILE_BYTES, ks * 16, Cfg::BOX_BYTES);
-          mma_ss(tmem + Cfg::TMEM_O, ad, bd, idesc_pv, (i > 0) || (ks > 0));
+          const uint64_t ao = (uint64_t)(((ks >> 2) * 16384 + (ks & 3) * 32) >> 4);
+          const uint64_t bo = (uint64_t)((ks * 16 * SW) >> 4);
+          mma_ss(tmem + Cfg::TMEM_O, pd + ao, vd + bo, idesc_pv, (i > 0) || (ks > 0));
         }
         mma_commit(&bars->v_empty[st]);
         mma_commit(&bars->p_empty[pbuf]);
-        if (i + 3 < T) issue_qk(i + 3);  // S ring slot i % 3 was released by p_full(i)
       }
-      mma_commit(&bars->o_full);
+      __syncwarp();
+      if (i + 3 < T) issue_qk(i + 3);  // S ring slot i % 3 was released by p_full(i)
     }
+    if (leader) mma_commit(&bars->o_full);
+    __syncwarp();
   } else if (warp >= 4) {
     // ---------------- silu warpgroups ----------------
     const int wg = (warp - 4) >> 2;

@@ -14,7 +14,8 @@ namespace hstu {
 constexpr int kNormThreads = 256;
 constexpr int kNormWarps = kNormThreads / 32;
 constexpr int kMaxPerLane = 32;     // 32 lanes * 32 = 1024 elements per normalised vector
-constexpr int kPartialRows = 2368;  // 148 SMs * 16 CTAs: enough warps in flight to cover HBM latency
+constexpr int kPartialRows = 592;   // backward: 148 SMs * 4 CTAs (each CTA emits one partial row of dw/db)
+constexpr int kFwdGridCap = 2368;   // forward: 148 SMs * 16 CTAs
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -444,10 +445,11 @@ __global__ void silu_kernel(const T* __restrict__ x, const T* __restrict__ dy, T
 // ------------------------------------------------------------------------------------------------
 static inline bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-static inline int norm_grid(long long n_vec) {
+static inline int norm_grid(long long n_vec, bool fwd = false) {
   long long need = (n_vec + kNormWarps - 1) / kNormWarps;
   if (need < 1) need = 1;
-  return (int)(need < kPartialRows ? need : kPartialRows);
+  const int cap = fwd ? kFwdGridCap : kPartialRows;
+  return (int)(need < cap ? need : cap);
 }
 
 template <typename T>
@@ -474,7 +476,7 @@ template <typename T>
 static int ln_fwd_t(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, long long n, int D,
                     long long xs, long long ys, float eps, int swish, bool rms, cudaStream_t st) {
   const bool v = can_vec<T>(D, {x, w, b, y}, {xs, ys});
-  const int grid = norm_grid(n);
+  const int grid = norm_grid(n, true);
   return dispatch_shape<T>(D, v, [&]<int VV, int PL>() -> int {
     if (rms)
       ln_fwd_kernel<T, VV, PL, true><<<grid, kNormThreads, 0, st>>>((const T*)x, (const T*)w, (const T*)b, (T*)y, mean,
@@ -561,7 +563,7 @@ static int nmd_fwd_t(const void* attn, const void* u, const void* w, const void*
   const int G = gn ? H : 1, len = gn ? dv : H * dv;
   // group norm: vectors start at head offsets g*len, and out rows at multiples of width -> need len % VEC == 0 (checked)
   const bool v = can_vec<T>(len, {attn, u, gn ? nullptr : w, gn ? nullptr : b, out}, {as, us});
-  const int grid = norm_grid(n * G);
+  const int grid = norm_grid(n * G, true);
   return dispatch_shape<T>(len, v, [&]<int VV, int PL>() -> int {
     nmd_fwd_kernel<T, VV, PL><<<grid, kNormThreads, 0, st>>>((const T*)attn, (const T*)u, (const T*)w, (const T*)b,
                                                              (T*)out, mean, rstd, n, G, len, as, us, eps, p, seed, silu_u,

@@ -241,12 +241,19 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   return r;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+#ifdef HSTU_EXP_NO_STS
+  if (saddr != 0xffffffffu) return;  // ablation experiment only
+#endif
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ float tanh_approx(float x) {
+#ifdef HSTU_EXP_NO_MUFU
+  return x * 0.25f;  // ablation experiment only (wrong numerics): takes the MUFU pipe out of the picture
+#else
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 // Byte offset of the 16-byte chunk `chunk` (0..SW/16-1) of row `row` inside a [rows][SW bytes] swizzled box whose base
