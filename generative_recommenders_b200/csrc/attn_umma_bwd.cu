@@ -311,8 +311,15 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
       const uint32_t st_addr = tmem + Cfg::TMEM_SLOT + slot * 128 + lane_bits;
       const uint32_t dp_addr = st_addr + 64;
+#ifdef HSTU_EXP_NO_ELEM
+      if (i >= 2) mbar_wait(&bars->pair_empty[i & 1], ((i >> 1) - 1) & 1);  // keep the protocol intact
+#endif
 #pragma unroll
+#ifdef HSTU_EXP_NO_ELEM
+      for (int c = 0; c < (T < 0 ? 2 : 0); ++c) {  // ablation experiment only
+#else
       for (int c = 0; c < 2; ++c) {  // 2 chunks of 32 query columns
+#endif
         uint32_t s[32], dp[32];
         tmem_ld32(st_addr + c * 32, s);
         tmem_ld32(dp_addr + c * 32, dp);

@@ -229,9 +229,17 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       const int mode = (n0 + 128 <= full_lim) ? 0 : (fast ? 1 : 2);  // tile-uniform: no divergence
       const int lim_rel = lim_i - n0, diag_rel = i_pos - n0;
       uint32_t sbuf[2][32];
+#ifdef HSTU_EXP_NO_ELEM
+      if (use >= 1) mbar_wait(&bars->p_empty[pbuf], (use - 1) & 1);  // keep the protocol intact
+      if (T < 0)  // ablation experiment only: skip the whole elementwise stage
+#endif
       tmem_ld32(s_taddr, sbuf[0]);
 #pragma unroll
+#ifdef HSTU_EXP_NO_ELEM
+      for (int c = 0; c < (T < 0 ? 4 : 0); ++c) {
+#else
       for (int c = 0; c < 4; ++c) {
+#endif
         tmem_ld_wait();
         if (c < 3) tmem_ld32(s_taddr + (c + 1) * 32, sbuf[(c + 1) & 1]);  // prefetch the next 32 columns
         const uint32_t(&s)[32] = sbuf[c & 1];

@@ -198,6 +198,9 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // 32 lanes x 32 consecutive columns: thread t of the warp gets TMEM lane (lane_base + t), columns [col, col+32).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+#ifdef HSTU_EXP_HALF_LDTM
+  if ((taddr & 32u) != 0) return;  // ablation experiment only: skip every other 32-column TMEM load (stale registers)
+#endif
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
