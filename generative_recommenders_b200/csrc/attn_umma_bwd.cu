@@ -51,31 +51,33 @@ struct BwdCfg {
   static constexpr int NBOX = D / BOX_COLS;
   static constexpr int BOX_BYTES = 128 * SW;
   static constexpr int TILE_BYTES = 128 * D * 2;
-  static constexpr int PT_BYTES = 128 * 128 * 2;
+  static constexpr int PT_BYTES = 128 * 128 * 2;          // one dS^T pair buffer: two [128 kv][64 q] boxes
+  static constexpr int STAGES = (D <= 32) ? 4 : 3;        // Q_i / dO_i TMA ring depth
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + TILE_BYTES;
-  static constexpr int STAGES = (D <= 32) ? 4 : 2;        // Q_i / dO_i TMA ring depth
   static constexpr int OFF_Q = OFF_V + TILE_BYTES;
   static constexpr int OFF_DO = OFF_Q + STAGES * TILE_BYTES;
-  static constexpr int OFF_PT = OFF_DO + STAGES * TILE_BYTES;
-  static constexpr int OFF_DST = OFF_PT + 2 * PT_BYTES;   // P^T and dS^T are double-buffered (tile i -> buffer i & 1)
+  static constexpr int OFF_DST = OFF_DO + STAGES * TILE_BYTES;   // dS^T boxes (tile i -> pair buffer i & 1)
   static constexpr int OFF_BAR = OFF_DST + 2 * PT_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   // TMEM: a ring of NSLOT score slots, each {S^T half-tile: 64 columns, dP^T half-tile: 64 columns} (a half-tile is
-  // 128 key rows x 64 query rows), followed by the dV, dK and dQ accumulators.
-  static constexpr int NSLOT = (384 + 3 * D <= 512) ? 3 : 2;
+  // 128 key rows x 64 query rows; after the elementwise stage the fronts of the two halves hold P^T and dS^T as bf16),
+  // the dV, dK and dQ accumulators, and K and V themselves as A operands (bf16, d/2 columns each).
+  static constexpr int NSLOT = (384 + 4 * D <= 512) ? 3 : 2;
   static constexpr int TMEM_SLOT = 0;
   static constexpr int TMEM_DV = NSLOT * 128;
   static constexpr int TMEM_DK = TMEM_DV + D;
   static constexpr int TMEM_DQ = TMEM_DK + D;
-  static_assert(TMEM_DQ + D <= 512, "TMEM budget");
+  static constexpr int TMEM_K = TMEM_DQ + D;
+  static constexpr int TMEM_V = TMEM_K + D / 2;
+  static_assert(TMEM_V + D / 2 <= 512, "TMEM budget");
   // scripts/sim_bwd_protocol.py: a 3-slot score ring needs the Q/dO ring to be at least 4 deep (the scores of tile i+2 are
   // requested before tile i releases its stage), otherwise the producer and the MMA issuer wait on each other.
   static_assert(NSLOT == 2 || STAGES >= 4, "3-slot score ring needs >= 4 Q/dO stages");
 };
 
 struct BwdBars {
-  uint64_t kv_full;
+  uint64_t kv_full, kvt_ready;
   uint64_t q_full[4], q_empty[4];
   uint64_t s_full[3], unit_done[4], pair_empty[2], dq_full, dq_empty, fin_full;
   uint32_t tmem_base;
@@ -114,13 +116,13 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
   uint8_t* sV = smem + Cfg::OFF_V;
   uint8_t* sQ = smem + Cfg::OFF_Q;
   uint8_t* sDO = smem + Cfg::OFF_DO;
-  uint8_t* sPT = smem + Cfg::OFF_PT;
   uint8_t* sDST = smem + Cfg::OFF_DST;
   BwdBars* bars = reinterpret_cast<BwdBars*>(smem + Cfg::OFF_BAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     mbar_init(&bars->kv_full, 1);
+    mbar_init(&bars->kvt_ready, 256);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->q_full[i], 1);
       mbar_init(&bars->q_empty[i], 1);
@@ -175,12 +177,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, BF16, BF16);    // S^T, dP^T half-tiles
     constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dV, dK: A K-major, B MN-major
     constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // dQ: A MN-major, B MN-major
-    const uint64_t dk_k = desc_kmajor<SW>(smem_u32(sK), 0);                        // K as K-major A (S^T)
-    const uint64_t dv_k = desc_kmajor<SW>(smem_u32(sV), 0);                        // V as K-major A (dP^T)
     const uint64_t dq_k = desc_kmajor<SW>(smem_u32(sQ), 0);                        // Q_i rows as K-major B
     const uint64_t ddo_k = desc_kmajor<SW>(smem_u32(sDO), 0);                      // dO_i rows as K-major B
-    const uint64_t dpt_k = desc_kmajor<128>(smem_u32(sPT), 0);                     // P^T box as K-major A
-    const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box as K-major A
     const uint64_t dds_mn = desc_mnmajor<128>(smem_u32(sDST), 0, 16384);           // dS^T pair as MN-major A (dQ)
     const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
     const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
@@ -200,19 +198,19 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         for (int ks = 0; ks < D / 16; ++ks) {
           const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
           const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
-          mma_ss(ts, dk_k + o, dq_k + row_off + o, idesc_s, ks > 0);
+          mma_ts(ts, tmem + Cfg::TMEM_K + ks * 8, dq_k + row_off + o, idesc_s, ks > 0);       // A = K from TMEM
         }
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
           const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
           const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
-          mma_ss(ts + 64, dv_k + o, ddo_k + row_off + o, idesc_s, ks > 0);
+          mma_ts(ts + 64, tmem + Cfg::TMEM_V + ks * 8, ddo_k + row_off + o, idesc_s, ks > 0);  // A = V from TMEM
         }
         mma_commit(&bars->s_full[slot]);
       }
       __syncwarp();
     };
-    mbar_wait(&bars->kv_full, 0);
+    mbar_wait(&bars->kvt_ready, 0);  // K and V have been copied into TMEM by the warpgroups
     tc_fence_after_sync();
     for (int u = 0; u < NSLOT && u < U; ++u) issue_s(u);
     for (int u = 0; u < U; ++u) {
@@ -222,27 +220,27 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       // then be two phases ahead and the parity wait would alias.
       mbar_wait(&bars->unit_done[hf * 2 + pb], (i >> 1) & 1);
       tc_fence_after_sync();
-      if (u + NSLOT < U) issue_s(u + NSLOT);   // refill the slot first: the other warpgroup is waiting for scores
-      const uint64_t box = (uint64_t)((pb * Cfg::PT_BYTES + hf * 16384) >> 4);
       const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);  // MN-major B: K rows = the 64 query rows
+      const uint32_t tp = tmem + Cfg::TMEM_SLOT + (u % NSLOT) * 128;                 // P^T at [0,32), dS^T at [64,96) of the slot
       if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
-          mma_ss(tmem + Cfg::TMEM_DV, dpt_k + box + (uint64_t)((ks * 32) >> 4), ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4),
-                 idesc_kv, (u > 0) || (ks > 0));
+        for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half; A = P^T from TMEM
+          mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (u > 0) || (ks > 0));
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          mma_ss(tmem + Cfg::TMEM_DK, dds_k + box + (uint64_t)((ks * 32) >> 4), dq_mn + rows + (uint64_t)((ks * 16 * SW) >> 4),
-                 idesc_kv, (u > 0) || (ks > 0));
+        for (int ks = 0; ks < 4; ++ks)  // A = dS^T from TMEM
+          mma_ts(tmem + Cfg::TMEM_DK, tp + 64 + ks * 8, dq_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (u > 0) || (ks > 0));
       }
       __syncwarp();
+      // refill the slot: issued after dV/dK of this unit, so the in-order tensor pipe has consumed P^T / dS^T before the
+      // next scores overwrite them
+      if (u + NSLOT < U) issue_s(u + NSLOT);
       if (hf == 1) {
         if (i >= 1) {
           mbar_wait(&bars->dq_empty, (i - 1) & 1);  // dQ_{i-1} has been drained from TMEM
           tc_fence_after_sync();
         }
         if (leader) {
-          const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);
+          const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);  // the dS^T boxes of this query tile in shared memory
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows; A = both boxes of the pair read MN-major (M = 128 query rows)
             mma_ss(tmem + Cfg::TMEM_DQ, dds_mn + pair + (uint64_t)((ks * 16 * 128) >> 4), dk_mn + (uint64_t)((ks * 16 * SW) >> 4),
@@ -269,6 +267,28 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     const bool j_hist = j_ok && (!msk.has_tgt || j_pos < msk.max_id);  // fast mask: valid = (j_hist & i > j) | (i == j)
     const int cbase = wg * 64;
     const int qcol0 = wg * (D / 2);                // dQ columns drained by this warpgroup
+
+    {
+      // K (warpgroup 0) / V (warpgroup 1) -> TMEM as bf16 A operands: row r of the tile = TMEM lane r, 16 elements per 8 columns
+      mbar_wait(&bars->kv_full, 0);
+      const uint8_t* src = (wg == 0 ? sK : sV);
+      const uint32_t dst = tmem + (wg == 0 ? Cfg::TMEM_K : Cfg::TMEM_V) + lane_bits;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {  // 32 elements = 64 bytes = 4 swizzled 16-byte chunks = 16 TMEM columns
+        uint32_t r[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int chunk = c * 4 + j;                        // 16-byte chunk index along the row
+          const int bx = chunk / (SW / 16), cc = chunk % (SW / 16);
+          const uint4 v = *reinterpret_cast<const uint4*>(src + bx * Cfg::BOX_BYTES + swizzled_chunk_offset<SW>(row, cc));
+          r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+        }
+        tmem_st16(dst + c * 16, r);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&bars->kvt_ready);
+    }
 
     auto drain_dq = [&](int i) {
       // dQ tile of query tile i: TMEM lane = query row -> fp32 vector reductions into dq_acc
@@ -305,7 +325,6 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       const int mh0 = m0 + cbase;                   // first query row of the half
       const bool full = fast && (mh0 >= n0 + 128) && (mh0 + 64 <= len) && (!msk.has_tgt || n0 + 128 <= msk.max_id);
       const int mode = full ? 0 : (fast ? 1 : 2);
-      const uint32_t sPTw = smem_u32(sPT + (i & 1) * Cfg::PT_BYTES + wg * 16384);
       const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + wg * 16384);
       const int jr = j_pos - m0 - cbase;           // query column (relative to this warpgroup's block) equal to j
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
@@ -378,13 +397,15 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         }
 #undef HSTU_BWD_ELEM
         if (c == 0 && i >= 2) mbar_wait(&bars->pair_empty[i & 1], ((i >> 1) - 1) & 1);  // GEMMs of tile i-2 are done with this buffer pair
+        // P^T / dS^T chunk c (32 bf16 = 16 columns) overwrite the already-read fronts of the S^T / dP^T halves of the slot
+        // (A operands of the dV / dK GEMMs); dS^T also goes to shared memory, where the dQ GEMM reads it transposed.
+        tmem_st16(st_addr + c * 16, pp);
+        tmem_st16(dp_addr + c * 16, dd);
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const uint32_t off = swizzled_chunk_offset<128>(row, c * 4 + j4);
-          st_shared_v4(sPTw + off, pp[4 * j4], pp[4 * j4 + 1], pp[4 * j4 + 2], pp[4 * j4 + 3]);
-          st_shared_v4(sDSTw + off, dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
-        }
+        for (int j4 = 0; j4 < 4; ++j4)
+          st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + j4), dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
       }
+      tmem_st_wait();
       tc_fence_before_sync();
       fence_proxy_async_smem();
       mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);

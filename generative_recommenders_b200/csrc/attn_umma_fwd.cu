@@ -43,16 +43,14 @@ struct FwdCfg {
   static constexpr int NBOX = D / BOX_COLS;
   static constexpr int BOX_BYTES = 128 * SW;
   static constexpr int TILE_BYTES = 128 * D * 2;
-  static constexpr int P_BYTES = 128 * 128 * 2;
-  static constexpr int STAGES = (D <= 32) ? 4 : 2;           // K / V TMA ring depth
+  static constexpr int STAGES = (D <= 64) ? 4 : 3;           // K / V TMA ring depth
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + TILE_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * TILE_BYTES;
-  static constexpr int OFF_P = OFF_V + STAGES * TILE_BYTES;
-  static constexpr int NPB = (D <= 64) ? 2 : 1;             // P buffers per silu warpgroup
-  static constexpr int OFF_BAR = OFF_P + 2 * NPB * P_BYTES;
+  static constexpr int OFF_BAR = OFF_V + STAGES * TILE_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
-  static constexpr int TMEM_S = 0;      // ring of 3 S buffers: columns [0,128), [128,256), [256,384)
+  // ring of 3 score slots of 128 columns; P (bf16 pairs, 64 columns) overwrites the front of its own S slot
+  static constexpr int TMEM_S = 0;
   static constexpr int TMEM_O = 384;    // O accumulator: columns [384, 384 + D)
   static_assert(384 + D <= 512, "TMEM budget");
 };
@@ -60,7 +58,7 @@ struct FwdCfg {
 struct FwdBars {
   uint64_t q_full;
   uint64_t k_full[4], k_empty[4], v_full[4], v_empty[4];
-  uint64_t s_full[3], p_full[4], p_empty[4];
+  uint64_t s_full[3], p_full[3];
   uint64_t o_full;
   uint32_t tmem_base;
 };
@@ -89,7 +87,6 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
   uint8_t* sQ = smem + Cfg::OFF_Q;
   uint8_t* sK = smem + Cfg::OFF_K;
   uint8_t* sV = smem + Cfg::OFF_V;
-  uint8_t* sP = smem + Cfg::OFF_P;
   FwdBars* bars = reinterpret_cast<FwdBars*>(smem + Cfg::OFF_BAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -101,11 +98,10 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       mbar_init(&bars->v_full[i], 1);
       mbar_init(&bars->v_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bars->s_full[i], 1);
       mbar_init(&bars->p_full[i], 128);
-      mbar_init(&bars->p_empty[i], 1);
     }
-    for (int i = 0; i < 3; ++i) mbar_init(&bars->s_full[i], 1);
     mbar_init(&bars->o_full, 1);
     fence_barrier_init();
   }
@@ -158,7 +154,6 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
     constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, BF16, BF16);
     const uint64_t dq0 = desc_kmajor<SW>(smem_u32(sQ), 0);
     const uint64_t dk0 = desc_kmajor<SW>(smem_u32(sK), 0);
-    const uint64_t dp0 = desc_kmajor<128>(smem_u32(sP), 0);
     const uint64_t dv0 = desc_mnmajor<SW>(smem_u32(sV), 0, Cfg::BOX_BYTES);
     auto issue_qk = [&](int i) {
       const int st = i % NST;
@@ -185,25 +180,21 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
     if (T > 1) issue_qk(1);
     if (T > 2) issue_qk(2);
     for (int i = 0; i < T; ++i) {
-      const int st = i % NST;
-      const int it = i >> 1, pbuf = (i & 1) * Cfg::NPB + (it % Cfg::NPB);  // P buffer of tile i (owned by warpgroup i & 1)
-      mbar_wait(&bars->p_full[pbuf], (it / Cfg::NPB) & 1);
+      const int st = i % NST, slot = i % 3;
+      mbar_wait(&bars->p_full[slot], (i / 3) & 1);   // P_i sits in TMEM (front of score slot i % 3)
       mbar_wait(&bars->v_full[st], (i / NST) & 1);
       tc_fence_after_sync();
-      const uint64_t pd = dp0 + (uint64_t)((pbuf * Cfg::P_BYTES) >> 4);
       const uint64_t vd = dv0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
+      const uint32_t tp = tmem + Cfg::TMEM_S + slot * 128;
       if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t ao = (uint64_t)(((ks >> 2) * 16384 + (ks & 3) * 32) >> 4);
-          const uint64_t bo = (uint64_t)((ks * 16 * SW) >> 4);
-          mma_ss(tmem + Cfg::TMEM_O, pd + ao, vd + bo, idesc_pv, (i > 0) || (ks > 0));
-        }
+        for (int ks = 0; ks < 8; ++ks)  // A = P from TMEM (16 bf16 of K per 8 columns), B = V read MN-major
+          mma_ts(tmem + Cfg::TMEM_O, tp + ks * 8, vd + (uint64_t)((ks * 16 * SW) >> 4), idesc_pv, (i > 0) || (ks > 0));
         mma_commit(&bars->v_empty[st]);
-        mma_commit(&bars->p_empty[pbuf]);
       }
       __syncwarp();
-      if (i + 3 < T) issue_qk(i + 3);  // S ring slot i % 3 was released by p_full(i)
+      // the tensor pipe executes this thread's MMAs in order: Q K_{i+3}^T overwrites slot i % 3 only after P_i V_i has read it
+      if (i + 3 < T) issue_qk(i + 3);
     }
     if (leader) mma_commit(&bars->o_full);
     __syncwarp();
@@ -223,14 +214,11 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       const uint32_t s_taddr = tmem + Cfg::TMEM_S + (i % 3) * 128 + lane_bits;
       mbar_wait(&bars->s_full[i % 3], (i / 3) & 1);
       tc_fence_after_sync();
-      const int pbuf = wg * Cfg::NPB + (it % Cfg::NPB), use = it / Cfg::NPB;
-      const uint32_t sPw = smem_u32(sP + pbuf * Cfg::P_BYTES);
       const int n0 = (t0 + i) * 128;
       const int mode = (n0 + 128 <= full_lim) ? 0 : (fast ? 1 : 2);  // tile-uniform: no divergence
       const int lim_rel = lim_i - n0, diag_rel = i_pos - n0;
       uint32_t sbuf[2][32];
 #ifdef HSTU_EXP_NO_ELEM
-      if (use >= 1) mbar_wait(&bars->p_empty[pbuf], (use - 1) & 1);  // keep the protocol intact
       if (T < 0)  // ablation experiment only: skip the whole elementwise stage
 #endif
       tmem_ld32(s_taddr, sbuf[0]);
@@ -272,17 +260,13 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
             pk[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
           }
         }
-        if (c == 0 && use >= 1) mbar_wait(&bars->p_empty[pbuf], (use - 1) & 1);  // the GEMM that last read this buffer is done
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const int cc = c * 4 + j4;  // 16-byte chunk index along the key dimension (0..15)
-          st_shared_v4(sPw + (cc >> 3) * 16384 + swizzled_chunk_offset<128>(row, cc & 7), pk[4 * j4], pk[4 * j4 + 1],
-                       pk[4 * j4 + 2], pk[4 * j4 + 3]);
-        }
+        // P chunk c (32 bf16 = 16 columns) goes to columns [16 c, 16 c + 16) of the slot: a region of S that has already
+        // been read (S chunk c covers columns [32 c, 32 c + 32))
+        tmem_st16(s_taddr + c * 16, pk);
       }
+      tmem_st_wait();
       tc_fence_before_sync();
-      fence_proxy_async_smem();
-      mbar_arrive(&bars->p_full[pbuf]);
+      mbar_arrive(&bars->p_full[i % 3]);
     }
     // ---------------- epilogue: O (TMEM) -> * 1/N -> global ----------------
     mbar_wait(&bars->o_full, 0);

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_umma.py tests/test_gpu_attention.py -m gpu -q --tb=short -p no:cacheprovider -x 2>&1 | tail -6 > gpurun_out/pytest8.log
+timeout 600 python -m pytest tests/test_gpu_umma.py tests/test_gpu_attention.py -m gpu -q --tb=short -p no:cacheprovider -x 2>&1 | tail -12 > gpurun_out/pytest8.log
 timeout 600 python bench.py --workload attn --steps 5 --warmup 3 --batch 16 --lmax 8192 --attn-dim 32 --attn-heads 8 --no-cpu-baseline > gpurun_out/bench_attn32.log 2>&1
 timeout 600 python bench.py --workload attn --steps 5 --warmup 3 --batch 64 --lmax 2048 --attn-dim 64 --no-cpu-baseline > gpurun_out/bench_attn64.log 2>&1
 timeout 600 python bench.py --workload attn --steps 5 --warmup 3 --batch 32 --lmax 4096 --attn-dim 128 --no-cpu-baseline > gpurun_out/bench_attn128.log 2>&1
