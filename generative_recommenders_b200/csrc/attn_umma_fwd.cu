@@ -51,8 +51,12 @@ struct FwdCfg {
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
   // ring of 3 score slots of 128 columns; P (bf16 pairs, 64 columns) overwrites the front of its own S slot
   static constexpr int TMEM_S = 0;
-  static constexpr int TMEM_O = 384;    // O accumulator: columns [384, 384 + D)
-  static_assert(384 + D <= 512, "TMEM budget");
+  // O is accumulated in NACC independent TMEM accumulators (k-step ks of every P.V goes to accumulator ks % NACC; they are
+  // summed in the epilogue): consecutive tcgen05.mma into ONE accumulator are dependent and expose the MMA latency when
+  // the instruction itself is short (N = d = 32: 16 clk of work).
+  static constexpr int NACC = (D <= 32) ? 4 : (D <= 64 ? 2 : 1);
+  static constexpr int TMEM_O = 384;    // accumulators: columns [384, 384 + NACC * D)
+  static_assert(384 + NACC * D <= 512, "TMEM budget");
 };
 
 struct FwdBars {
@@ -123,6 +127,12 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       for (int i = 0; i < T; ++i) {
         const int st = i % NST;
         if (i >= NST) mbar_wait(&bars->k_empty[st], ((i / NST) - 1) & 1);
+#ifdef HSTU_EXP_NO_KLOAD
+        if (i >= NST) {  // ablation experiment only
+          mbar_arrive(&bars->k_full[st]);
+          continue;
+        }
+#endif
         mbar_arrive_expect_tx(&bars->k_full[st], Cfg::TILE_BYTES);
 #pragma unroll
         for (int bx = 0; bx < Cfg::NBOX; ++bx)
@@ -137,6 +147,12 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       for (int i = 0; i < T; ++i) {
         const int st = i % NST;
         if (i >= NST) mbar_wait(&bars->v_empty[st], ((i / NST) - 1) & 1);
+#ifdef HSTU_EXP_NO_VLOAD
+        if (i >= NST) {  // ablation experiment only: no TMA traffic for V after the ring has been filled once
+          mbar_arrive(&bars->v_full[st]);
+          continue;
+        }
+#endif
         mbar_arrive_expect_tx(&bars->v_full[st], Cfg::TILE_BYTES);
 #pragma unroll
         for (int bx = 0; bx < Cfg::NBOX; ++bx)
@@ -189,7 +205,8 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)  // A = P from TMEM (16 bf16 of K per 8 columns), B = V read MN-major
-          mma_ts(tmem + Cfg::TMEM_O, tp + ks * 8, vd + (uint64_t)((ks * 16 * SW) >> 4), idesc_pv, (i > 0) || (ks > 0));
+          mma_ts(tmem + Cfg::TMEM_O + (ks % Cfg::NACC) * D, tp + ks * 8, vd + (uint64_t)((ks * 16 * SW) >> 4), idesc_pv,
+                 (i > 0) || (ks >= Cfg::NACC));
         mma_commit(&bars->v_empty[st]);
       }
       __syncwarp();
@@ -279,6 +296,14 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       uint32_t o[16];
       tmem_ld16(tmem + Cfg::TMEM_O + cbase + c * 16 + lane_bits, o);
       tmem_ld_wait();
+#pragma unroll
+      for (int a = 1; a < Cfg::NACC; ++a) {  // sum the independent accumulators
+        uint32_t o2[16];
+        tmem_ld16(tmem + Cfg::TMEM_O + a * D + cbase + c * 16 + lane_bits, o2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) + __uint_as_float(o2[e]));
+      }
       if (row < mrows) {
         uint32_t pk[8];
 #pragma unroll

@@ -185,6 +185,82 @@ __global__ void mufu_bench_kernel(float* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = a + b + c + d + __uint_as_float(pa) + __uint_as_float(pb);
 }
 
+static void rep(char* buf, size_t cap, const char* fmt, ...);
+
+// ---- tcgen05.mma issue-rate / latency micro-benchmark --------------------------------------------
+// One thread issues `count` MMAs (M = 128, K = 16) back to back, commits, and waits; cycles are read with clock64().
+// mode bit 0: A from TMEM (TS) instead of shared memory; `nacc`: number of accumulators the MMAs rotate over.
+__global__ void __launch_bounds__(128) umma_rate_kernel(int N, int mode, int nacc, int count, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw2[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, N, false, false, true, true);
+    const uint64_t ad = desc_kmajor<128>(smem_u32(smem), 0);
+    const uint64_t bd = desc_kmajor<128>(smem_u32(smem) + 32768, 0);
+    // latency of one MMA: issue -> commit -> barrier observed
+    long long t0 = clock64();
+    mma_ss(tmem, ad, bd, idesc, 0);
+    mma_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    const uint32_t acc_stride = nacc > 1 ? (uint32_t)N : 0u;
+    if (mode & 1) {
+      for (int i = 0; i < count; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mma_ts(tmem + (j & 3) * acc_stride, tmem + 448, bd + (uint64_t)((j & 3) * 2), idesc, 1);
+      }
+    } else {
+      for (int i = 0; i < count; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          mma_ss(tmem + (j & 3) * acc_stride, ad + (uint64_t)((j & 3) * 2), bd + (uint64_t)((j & 3) * 2), idesc, 1);
+      }
+    }
+    long long t2 = clock64();
+    mma_commit(&bar);
+    mbar_wait(&bar, 1);
+    long long t3 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t1;
+    out[2] = t3 - t1;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static void rate_case(const char* name, int N, int mode, int nacc, char* report, size_t cap) {
+  long long* d = nullptr;
+  long long h[3] = {0, 0, 0};
+  const int count = 2048;
+  cudaMalloc(&d, sizeof(h));
+  cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  umma_rate_kernel<<<1, 128, 66560>>>(N, mode, nacc, count, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    rep(report, cap, "mma-rate/%-26s CUDA-ERROR %s\n", name, cudaGetErrorString(e));
+    return;
+  }
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  rep(report, cap, "mma-rate/%-26s single MMA round trip %5lld clk; %d MMAs: issue %6.1f clk/MMA, complete %6.1f clk/MMA\n", name,
+      h[0], count, (double)h[1] / count, (double)h[2] / count);
+}
+
 static void rep(char* buf, size_t cap, const char* fmt, ...) {
   size_t n = strlen(buf);
   if (n + 1 >= cap) return;
@@ -331,6 +407,15 @@ int umma_selftest(char* report, size_t cap) {
     }
     if (c.cfg.variant == 0) fails += r;  // diagnostic variants do not count
   }
+  rate_case("SS N=128 1 acc", 128, 0, 1, report, cap);
+  rate_case("SS N=256 1 acc", 256, 0, 1, report, cap);
+  rate_case("SS N=64 1 acc", 64, 0, 1, report, cap);
+  rate_case("SS N=32 1 acc", 32, 0, 1, report, cap);
+  rate_case("SS N=32 4 acc", 32, 0, 4, report, cap);
+  rate_case("TS N=32 1 acc", 32, 1, 1, report, cap);
+  rate_case("TS N=32 4 acc", 32, 1, 4, report, cap);
+  rate_case("TS N=64 1 acc", 64, 1, 1, report, cap);
+  rate_case("TS N=128 1 acc", 128, 1, 1, report, cap);
   mufu_case<0>("tanh.approx.f32", 4, report, cap);
   mufu_case<1>("ex2+rcp f32 (sigmoid)", 2, report, cap);
   mufu_case<2>("tanh.approx.bf16x2", 4, report, cap);
