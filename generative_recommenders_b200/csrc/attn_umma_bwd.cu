@@ -51,13 +51,14 @@ struct BwdCfg {
   static constexpr int NBOX = D / BOX_COLS;
   static constexpr int BOX_BYTES = 128 * SW;
   static constexpr int TILE_BYTES = 128 * D * 2;
-  static constexpr int PT_BYTES = 128 * 128 * 2;          // one dS^T pair buffer: two [128 kv][64 q] boxes
-  static constexpr int STAGES = (D <= 32) ? 4 : 3;        // Q_i / dO_i TMA ring depth
+  static constexpr int PT_BYTES = 128 * 128 * 2;          // one pair buffer: two [128 kv][64 q] boxes
+  static constexpr int STAGES = (D <= 32) ? 4 : 2;        // Q_i / dO_i TMA ring depth
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + TILE_BYTES;
   static constexpr int OFF_Q = OFF_V + TILE_BYTES;
   static constexpr int OFF_DO = OFF_Q + STAGES * TILE_BYTES;
-  static constexpr int OFF_DST = OFF_DO + STAGES * TILE_BYTES;   // dS^T boxes (tile i -> pair buffer i & 1)
+  static constexpr int OFF_PT = OFF_DO + STAGES * TILE_BYTES;    // P^T boxes  (tile i -> pair buffer i & 1)
+  static constexpr int OFF_DST = OFF_PT + 2 * PT_BYTES;          // dS^T boxes
   static constexpr int OFF_BAR = OFF_DST + 2 * PT_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   // TMEM: a ring of NSLOT score slots, each {S^T half-tile: 64 columns, dP^T half-tile: 64 columns} (a half-tile is
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
   uint8_t* sV = smem + Cfg::OFF_V;
   uint8_t* sQ = smem + Cfg::OFF_Q;
   uint8_t* sDO = smem + Cfg::OFF_DO;
+  uint8_t* sPT = smem + Cfg::OFF_PT;
   uint8_t* sDST = smem + Cfg::OFF_DST;
   BwdBars* bars = reinterpret_cast<BwdBars*>(smem + Cfg::OFF_BAR);
 
@@ -175,17 +177,19 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     constexpr int NSLOT = Cfg::NSLOT;
     const bool leader = lane == 0;
     constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, BF16, BF16);    // S^T, dP^T half-tiles
-    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dV, dK: A K-major, B MN-major
-    constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // dQ: A MN-major, B MN-major
     const uint64_t dq_k = desc_kmajor<SW>(smem_u32(sQ), 0);                        // Q_i rows as K-major B
     const uint64_t ddo_k = desc_kmajor<SW>(smem_u32(sDO), 0);                      // dO_i rows as K-major B
-    const uint64_t dds_mn = desc_mnmajor<128>(smem_u32(sDST), 0, 16384);           // dS^T pair as MN-major A (dQ)
-    const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
-    const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
-    const uint64_t dk_mn = desc_mnmajor<SW>(smem_u32(sK), 0, Cfg::BOX_BYTES);      // K as MN-major B (dQ)
     const int U = 2 * T;
-    auto issue_s = [&](int u) {
+    // ---- issuer X (this warp): the score GEMMs S^T, dP^T of every unit, as soon as their TMEM slot is free ----
+    mbar_wait(&bars->kvt_ready, 0);  // K and V have been copied into TMEM by the warpgroups
+    tc_fence_after_sync();
+    for (int u = 0; u < U; ++u) {
       const int i = u >> 1, hf = u & 1, st = i % NST, slot = u % NSLOT;
+      if (u >= NSLOT) {  // the warpgroup has finished reading unit u - NSLOT out of this slot
+        const int up = u - NSLOT, ip = up >> 1;
+        mbar_wait(&bars->unit_done[(up & 1) * 2 + (ip & 1)], (ip >> 1) & 1);
+        tc_fence_after_sync();
+      }
       if (hf == 0) {
         mbar_wait(&bars->q_full[st], (i / NST) & 1);
         tc_fence_after_sync();
@@ -209,31 +213,42 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         mma_commit(&bars->s_full[slot]);
       }
       __syncwarp();
-    };
-    mbar_wait(&bars->kvt_ready, 0);  // K and V have been copied into TMEM by the warpgroups
-    tc_fence_after_sync();
-    for (int u = 0; u < NSLOT && u < U; ++u) issue_s(u);
+    }
+  } else if (warp == 2) {
+    // ---- issuer Y: the gradient GEMMs dV, dK (per unit) and dQ (per query tile).  A second issuing thread keeps the
+    // tensor pipe fed while issuer X sits in a barrier wait (each tcgen05.mma blocks its issuer ~45 clk; measured). ----
+    constexpr int NSLOT = Cfg::NSLOT;
+    (void)NSLOT;
+    const bool leader = lane == 0;
+    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dV, dK: A K-major, B MN-major
+    constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // dQ: A MN-major, B MN-major
+    const uint64_t dpt_k = desc_kmajor<128>(smem_u32(sPT), 0);                     // P^T box as K-major A
+    const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box as K-major A
+    const uint64_t dds_mn = desc_mnmajor<128>(smem_u32(sDST), 0, 16384);           // dS^T pair as MN-major A (dQ)
+    const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
+    const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
+    const uint64_t dk_mn = desc_mnmajor<SW>(smem_u32(sK), 0, Cfg::BOX_BYTES);      // K as MN-major B (dQ)
+    const int U = 2 * T;
     for (int u = 0; u < U; ++u) {
       const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1;
-      // box (pb, hf) of P^T / dS^T is written and slot u % NSLOT has been read.  One barrier per (half, tile parity): with a
-      // 3-slot score ring a warpgroup may finish TWO units before this thread gets here; a single barrier per half would
-      // then be two phases ahead and the parity wait would alias.
+      // box (pb, hf) of P^T / dS^T is written.  One barrier per (half, tile parity): with a 3-slot score ring a warpgroup
+      // may finish TWO units before this thread gets here; a single barrier per half would then be two phases ahead and
+      // the parity wait would alias.
       mbar_wait(&bars->unit_done[hf * 2 + pb], (i >> 1) & 1);
       tc_fence_after_sync();
+      const uint64_t box = (uint64_t)((pb * Cfg::PT_BYTES + hf * 16384) >> 4);
       const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);  // MN-major B: K rows = the 64 query rows
-      const uint32_t tp = tmem + Cfg::TMEM_SLOT + (u % NSLOT) * 128;                 // P^T at [0,32), dS^T at [64,96) of the slot
       if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half; A = P^T from TMEM
-          mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (u > 0) || (ks > 0));
+        for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
+          mma_ss(tmem + Cfg::TMEM_DV, dpt_k + box + (uint64_t)((ks * 32) >> 4), ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4),
+                 idesc_kv, (u > 0) || (ks > 0));
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)  // A = dS^T from TMEM
-          mma_ts(tmem + Cfg::TMEM_DK, tp + 64 + ks * 8, dq_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (u > 0) || (ks > 0));
+        for (int ks = 0; ks < 4; ++ks)
+          mma_ss(tmem + Cfg::TMEM_DK, dds_k + box + (uint64_t)((ks * 32) >> 4), dq_mn + rows + (uint64_t)((ks * 16 * SW) >> 4),
+                 idesc_kv, (u > 0) || (ks > 0));
       }
       __syncwarp();
-      // refill the slot: issued after dV/dK of this unit, so the in-order tensor pipe has consumed P^T / dS^T before the
-      // next scores overwrite them
-      if (u + NSLOT < U) issue_s(u + NSLOT);
       if (hf == 1) {
         if (i >= 1) {
           mbar_wait(&bars->dq_empty, (i - 1) & 1);  // dQ_{i-1} has been drained from TMEM
@@ -245,6 +260,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
           for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows; A = both boxes of the pair read MN-major (M = 128 query rows)
             mma_ss(tmem + Cfg::TMEM_DQ, dds_mn + pair + (uint64_t)((ks * 16 * 128) >> 4), dk_mn + (uint64_t)((ks * 16 * SW) >> 4),
                    idesc_dq, ks > 0);
+          // both issuers' GEMMs on this Q_i / dO_i stage are complete here: the scores of the tile were consumed by the
+          // warpgroups before unit_done, and everything this thread issued is covered by the commit
           mma_commit(&bars->q_empty[st]);
           mma_commit(&bars->pair_empty[pb]);
           mma_commit(&bars->dq_full);
@@ -325,6 +342,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       const int mh0 = m0 + cbase;                   // first query row of the half
       const bool full = fast && (mh0 >= n0 + 128) && (mh0 + 64 <= len) && (!msk.has_tgt || n0 + 128 <= msk.max_id);
       const int mode = full ? 0 : (fast ? 1 : 2);
+      const uint32_t sPTw = smem_u32(sPT + (i & 1) * Cfg::PT_BYTES + wg * 16384);
       const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + wg * 16384);
       const int jr = j_pos - m0 - cbase;           // query column (relative to this warpgroup's block) equal to j
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
@@ -397,15 +415,13 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         }
 #undef HSTU_BWD_ELEM
         if (c == 0 && i >= 2) mbar_wait(&bars->pair_empty[i & 1], ((i >> 1) - 1) & 1);  // GEMMs of tile i-2 are done with this buffer pair
-        // P^T / dS^T chunk c (32 bf16 = 16 columns) overwrite the already-read fronts of the S^T / dP^T halves of the slot
-        // (A operands of the dV / dK GEMMs); dS^T also goes to shared memory, where the dQ GEMM reads it transposed.
-        tmem_st16(st_addr + c * 16, pp);
-        tmem_st16(dp_addr + c * 16, dd);
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4)
-          st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + j4), dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const uint32_t off = swizzled_chunk_offset<128>(row, c * 4 + j4);
+          st_shared_v4(sPTw + off, pp[4 * j4], pp[4 * j4 + 1], pp[4 * j4 + 2], pp[4 * j4 + 3]);
+          st_shared_v4(sDSTw + off, dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
+        }
       }
-      tmem_st_wait();
       tc_fence_before_sync();
       fence_proxy_async_smem();
       mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);
