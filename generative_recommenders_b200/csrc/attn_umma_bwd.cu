@@ -57,9 +57,9 @@ struct BwdCfg {
   static constexpr int OFF_V = OFF_K + TILE_BYTES;
   static constexpr int OFF_Q = OFF_V + TILE_BYTES;
   static constexpr int OFF_DO = OFF_Q + STAGES * TILE_BYTES;
-  static constexpr int OFF_PT = OFF_DO + STAGES * TILE_BYTES;    // P^T boxes  (tile i -> pair buffer i & 1)
-  static constexpr int OFF_DST = OFF_PT + 2 * PT_BYTES;          // dS^T boxes
-  static constexpr int OFF_BAR = OFF_DST + 2 * PT_BYTES;
+  static constexpr int OFF_DST = OFF_DO + STAGES * TILE_BYTES;   // dS^T boxes [kv][q] (tile i -> pair buffer i & 1): A of dK
+  static constexpr int OFF_DS = OFF_DST + 2 * PT_BYTES;          // dS   boxes [q][kv]: A of dQ (K-major; an MN-major A costs ~4x)
+  static constexpr int OFF_BAR = OFF_DS + 2 * PT_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   // TMEM: a ring of NSLOT score slots, each {S^T half-tile: 64 columns, dP^T half-tile: 64 columns} (a half-tile is
   // 128 key rows x 64 query rows; after the elementwise stage the fronts of the two halves hold P^T and dS^T as bf16),
@@ -83,6 +83,18 @@ struct BwdBars {
   uint64_t s_full[3], unit_done[4], pair_empty[2], dq_full, dq_empty, fin_full;
   uint32_t tmem_base;
 };
+
+#ifdef HSTU_TRACE
+// Debug timeline: CTA (0,0,0) records clock64() stamps of its pipeline events into g_trace[role][index][slot].
+__device__ long long* g_trace = nullptr;
+#define HSTU_TSTAMP(role, idx, k)                                                                              \
+  do {                                                                                                           \
+    if (g_trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 256)                \
+      g_trace[((role) * 256 + (idx)) * 4 + (k)] = clock64();                                                     \
+  } while (0)
+#else
+#define HSTU_TSTAMP(role, idx, k) do { } while (0)
+#endif
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -117,8 +129,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
   uint8_t* sV = smem + Cfg::OFF_V;
   uint8_t* sQ = smem + Cfg::OFF_Q;
   uint8_t* sDO = smem + Cfg::OFF_DO;
-  uint8_t* sPT = smem + Cfg::OFF_PT;
   uint8_t* sDST = smem + Cfg::OFF_DST;
+  uint8_t* sDS = smem + Cfg::OFF_DS;
   BwdBars* bars = reinterpret_cast<BwdBars*>(smem + Cfg::OFF_BAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -127,14 +139,14 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     mbar_init(&bars->kvt_ready, 256);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->q_full[i], 1);
-      mbar_init(&bars->q_empty[i], 1);
+      mbar_init(&bars->q_empty[i], 2);  // both MMA issuers release a Q/dO stage
     }
     for (int i = 0; i < 3; ++i) mbar_init(&bars->s_full[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bars->unit_done[i], 128);
     for (int i = 0; i < 2; ++i) mbar_init(&bars->pair_empty[i], 1);
     mbar_init(&bars->dq_full, 1);
     mbar_init(&bars->dq_empty, 256);
-    mbar_init(&bars->fin_full, 1);
+    mbar_init(&bars->fin_full, 2);     // both MMA issuers
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
@@ -177,19 +189,35 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     constexpr int NSLOT = Cfg::NSLOT;
     const bool leader = lane == 0;
     constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, BF16, BF16);    // S^T, dP^T half-tiles
+    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dV: A = P^T (TMEM), B MN-major
     const uint64_t dq_k = desc_kmajor<SW>(smem_u32(sQ), 0);                        // Q_i rows as K-major B
     const uint64_t ddo_k = desc_kmajor<SW>(smem_u32(sDO), 0);                      // dO_i rows as K-major B
+    const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
     const int U = 2 * T;
+    // dV += P^T dO for unit up: A = P^T from the front of the unit's TMEM slot (written by the warpgroup over S^T)
+    auto issue_dv = [&](int up) {
+      const int ip = up >> 1, hp = up & 1, stp = ip % NST;
+      mbar_wait(&bars->unit_done[hp * 2 + (ip & 1)], (ip >> 1) & 1);
+      tc_fence_after_sync();
+      const uint64_t rows = (uint64_t)((stp * Cfg::TILE_BYTES + hp * 64 * SW) >> 4);
+      const uint32_t tp = tmem + Cfg::TMEM_SLOT + (up % NSLOT) * 128;
+      if (leader) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
+          mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (up > 0) || (ks > 0));
+        if (hp == 1) mma_commit(&bars->q_empty[stp]);  // this issuer is done with stage stp (scores and dV of both halves)
+      }
+      __syncwarp();
+    };
     // ---- issuer X (this warp): the score GEMMs S^T, dP^T of every unit, as soon as their TMEM slot is free ----
     mbar_wait(&bars->kvt_ready, 0);  // K and V have been copied into TMEM by the warpgroups
     tc_fence_after_sync();
     for (int u = 0; u < U; ++u) {
       const int i = u >> 1, hf = u & 1, st = i % NST, slot = u % NSLOT;
-      if (u >= NSLOT) {  // the warpgroup has finished reading unit u - NSLOT out of this slot
-        const int up = u - NSLOT, ip = up >> 1;
-        mbar_wait(&bars->unit_done[(up & 1) * 2 + (ip & 1)], (ip >> 1) & 1);
-        tc_fence_after_sync();
-      }
+      if (leader) HSTU_TSTAMP(0, u, 0);
+      // the slot still holds P^T of unit u - NSLOT: consume it (dV) first; the in-order tensor pipe then lets the new
+      // scores overwrite it
+      if (u >= NSLOT) issue_dv(u - NSLOT);
       if (hf == 0) {
         mbar_wait(&bars->q_full[st], (i / NST) & 1);
         tc_fence_after_sync();
@@ -198,6 +226,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       const uint64_t row_off = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);
       const uint32_t ts = tmem + Cfg::TMEM_SLOT + slot * 128;
       if (leader) {
+        HSTU_TSTAMP(0, u, 1);
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
           const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
@@ -211,21 +240,22 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
           mma_ts(ts + 64, tmem + Cfg::TMEM_V + ks * 8, ddo_k + row_off + o, idesc_s, ks > 0);  // A = V from TMEM
         }
         mma_commit(&bars->s_full[slot]);
+        HSTU_TSTAMP(0, u, 2);
       }
       __syncwarp();
     }
+    for (int up = (U > NSLOT ? U - NSLOT : 0); up < U; ++up) issue_dv(up);
+    if (leader) mma_commit(&bars->fin_full);
+    __syncwarp();
   } else if (warp == 2) {
     // ---- issuer Y: the gradient GEMMs dV, dK (per unit) and dQ (per query tile).  A second issuing thread keeps the
     // tensor pipe fed while issuer X sits in a barrier wait (each tcgen05.mma blocks its issuer ~45 clk; measured). ----
     constexpr int NSLOT = Cfg::NSLOT;
     (void)NSLOT;
     const bool leader = lane == 0;
-    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dV, dK: A K-major, B MN-major
-    constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // dQ: A MN-major, B MN-major
-    const uint64_t dpt_k = desc_kmajor<128>(smem_u32(sPT), 0);                     // P^T box as K-major A
-    const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box as K-major A
-    const uint64_t dds_mn = desc_mnmajor<128>(smem_u32(sDST), 0, 16384);           // dS^T pair as MN-major A (dQ)
-    const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
+    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dK, dQ: A K-major, B MN-major
+    const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box [kv][q] as K-major A (dK)
+    const uint64_t dsq_k = desc_kmajor<128>(smem_u32(sDS), 0);                     // dS boxes [q][kv] as K-major A (dQ)
     const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
     const uint64_t dk_mn = desc_mnmajor<SW>(smem_u32(sK), 0, Cfg::BOX_BYTES);      // K as MN-major B (dQ)
     const int U = 2 * T;
@@ -234,20 +264,19 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       // box (pb, hf) of P^T / dS^T is written.  One barrier per (half, tile parity): with a 3-slot score ring a warpgroup
       // may finish TWO units before this thread gets here; a single barrier per half would then be two phases ahead and
       // the parity wait would alias.
+      if (leader) HSTU_TSTAMP(1, u, 0);
       mbar_wait(&bars->unit_done[hf * 2 + pb], (i >> 1) & 1);
       tc_fence_after_sync();
+      if (leader) HSTU_TSTAMP(1, u, 1);
       const uint64_t box = (uint64_t)((pb * Cfg::PT_BYTES + hf * 16384) >> 4);
       const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);  // MN-major B: K rows = the 64 query rows
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
-          mma_ss(tmem + Cfg::TMEM_DV, dpt_k + box + (uint64_t)((ks * 32) >> 4), ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4),
-                 idesc_kv, (u > 0) || (ks > 0));
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
           mma_ss(tmem + Cfg::TMEM_DK, dds_k + box + (uint64_t)((ks * 32) >> 4), dq_mn + rows + (uint64_t)((ks * 16 * SW) >> 4),
                  idesc_kv, (u > 0) || (ks > 0));
       }
+      if (leader) HSTU_TSTAMP(1, u, 2);
       __syncwarp();
       if (hf == 1) {
         if (i >= 1) {
@@ -255,13 +284,12 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
           tc_fence_after_sync();
         }
         if (leader) {
-          const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);  // the dS^T boxes of this query tile in shared memory
+          HSTU_TSTAMP(1, u, 3);
+          const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);  // the dS boxes of this query tile in shared memory
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows; A = both boxes of the pair read MN-major (M = 128 query rows)
-            mma_ss(tmem + Cfg::TMEM_DQ, dds_mn + pair + (uint64_t)((ks * 16 * 128) >> 4), dk_mn + (uint64_t)((ks * 16 * SW) >> 4),
-                   idesc_dq, ks > 0);
-          // both issuers' GEMMs on this Q_i / dO_i stage are complete here: the scores of the tile were consumed by the
-          // warpgroups before unit_done, and everything this thread issued is covered by the commit
+          for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows: box ks / 4 holds keys [64 (ks/4), +64), 32 bytes per k-step
+            mma_ss(tmem + Cfg::TMEM_DQ, dsq_k + pair + (uint64_t)(((ks >> 2) * 16384 + (ks & 3) * 32) >> 4),
+                   dk_mn + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, ks > 0);
           mma_commit(&bars->q_empty[st]);
           mma_commit(&bars->pair_empty[pb]);
           mma_commit(&bars->dq_full);
@@ -336,13 +364,17 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     for (int i = 0; i < T; ++i) {
       const int u = 2 * i + wg, slot = u % Cfg::NSLOT;
       const int m0 = q_tile(i) * 128;
+      if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 0);
       mbar_wait(&bars->s_full[slot], (u / Cfg::NSLOT) & 1);
       tc_fence_after_sync();
+      if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 1);
       // classification of this half-tile (uniform over the warpgroup)
       const int mh0 = m0 + cbase;                   // first query row of the half
       const bool full = fast && (mh0 >= n0 + 128) && (mh0 + 64 <= len) && (!msk.has_tgt || n0 + 128 <= msk.max_id);
       const int mode = full ? 0 : (fast ? 1 : 2);
-      const uint32_t sPTw = smem_u32(sPT + (i & 1) * Cfg::PT_BYTES + wg * 16384);
+      // dS box of this key row: keys [0,64) -> box 0, [64,128) -> box 1; 16-byte chunk (row % 64) / 8, 2 bytes at (row % 8) * 2
+      const uint32_t sDSw = smem_u32(sDS + (i & 1) * Cfg::PT_BYTES + (row >> 6) * 16384) + (row & 7) * 2;
+      const uint32_t ds_chunk = (uint32_t)((row & 63) >> 3);
       const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + wg * 16384);
       const int jr = j_pos - m0 - cbase;           // query column (relative to this warpgroup's block) equal to j
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
@@ -415,17 +447,26 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         }
 #undef HSTU_BWD_ELEM
         if (c == 0 && i >= 2) mbar_wait(&bars->pair_empty[i & 1], ((i >> 1) - 1) & 1);  // GEMMs of tile i-2 are done with this buffer pair
+        // P^T chunk c (32 bf16 = 16 columns) overwrites the already-read front of the S^T half of the slot: A of the dV GEMM
+        tmem_st16(st_addr + c * 16, pp);
+        // dS^T [kv][q] (16-byte stores, A of dK) and dS [q][kv] (2-byte stores, A of dQ)
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const uint32_t off = swizzled_chunk_offset<128>(row, c * 4 + j4);
-          st_shared_v4(sPTw + off, pp[4 * j4], pp[4 * j4 + 1], pp[4 * j4 + 2], pp[4 * j4 + 3]);
-          st_shared_v4(sDSTw + off, dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
+        for (int j4 = 0; j4 < 4; ++j4)
+          st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + j4), dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const uint32_t qrow = (uint32_t)(cbase + c * 32 + e);                  // query row of the 128-row tile
+          const uint32_t a = sDSw + qrow * 128 + ((ds_chunk ^ (qrow & 7)) << 4);
+          st_shared_b16(a, (e & 1) ? (dd[e >> 1] >> 16) : dd[e >> 1]);
         }
       }
+      tmem_st_wait();
       tc_fence_before_sync();
       fence_proxy_async_smem();
+      if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 2);
       mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);
       if (i >= 1) drain_dq(i - 1);
+      if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 3);
     }
     drain_dq(T - 1);
     // ---------------- epilogue: dV (warpgroup 0) / dK (warpgroup 1): TMEM -> scale -> global ----------------
@@ -548,8 +589,34 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   auto kern = attn_bwd_umma_kernel<D, BF16>;
   HSTU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   dim3 grid((p.max_seq_len + 127) / 128, p.heads, p.batch);
+#ifdef HSTU_TRACE
+  long long* tbuf = nullptr;
+  const size_t tbytes = sizeof(long long) * 4 * 256 * 4;
+  cudaMalloc(&tbuf, tbytes);
+  cudaMemset(tbuf, 0, tbytes);
+  cudaMemcpyToSymbol(g_trace, &tbuf, sizeof(tbuf));
+#endif
   kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(bp);
   HSTU_CUDA_OK(cudaGetLastError());
+#ifdef HSTU_TRACE
+  {
+    cudaDeviceSynchronize();
+    static long long host[4 * 256 * 4];
+    cudaMemcpy(host, tbuf, tbytes, cudaMemcpyDeviceToHost);
+    FILE* f = fopen("gpurun_out/bwd_trace.txt", "w");
+    if (f) {
+      for (int r = 0; r < 4; ++r)
+        for (int i = 0; i < 256; ++i) {
+          const long long* e = host + (r * 256 + i) * 4;
+          if (e[0] || e[1] || e[2] || e[3]) fprintf(f, "%d %d %lld %lld %lld %lld\n", r, i, e[0], e[1], e[2], e[3]);
+        }
+      fclose(f);
+    }
+    cudaFree(tbuf);
+    tbuf = nullptr;
+    cudaMemcpyToSymbol(g_trace, &tbuf, sizeof(tbuf));
+  }
+#endif
   const long long nvec = p.total_rows * p.heads * (D / 8);
   long long blocks = (nvec + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;

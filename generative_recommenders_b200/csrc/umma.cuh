@@ -249,6 +249,9 @@ __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_
 #endif
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void st_shared_b16(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)v) : "memory");
+}
 __device__ __forceinline__ float tanh_approx(float x) {
 #ifdef HSTU_EXP_NO_MUFU
   return x * 0.25f;  // ablation experiment only (wrong numerics): takes the MUFU pipe out of the picture
