@@ -208,9 +208,12 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int N, int mode, int nac
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   if (tid == 0) {
-    const uint32_t idesc = make_idesc(128, N, false, false, true, true);
-    const uint64_t ad = desc_kmajor<128>(smem_u32(smem), 0);
-    const uint64_t bd = desc_kmajor<128>(smem_u32(smem) + 32768, 0);
+    const int amode = mode & 3, bmode = (mode >> 2) & 3;
+    const uint32_t idesc = make_idesc(128, N, amode == 2, bmode >= 2, true, true);
+    const uint32_t sa = smem_u32(smem), sb = smem_u32(smem) + 32768;
+    const uint64_t ad = amode == 2 ? desc_mnmajor<128>(sa, 0, 16384) : amode == 3 ? desc_kmajor<64>(sa, 0) : desc_kmajor<128>(sa, 0);
+    const uint64_t bd = bmode == 0 ? desc_kmajor<128>(sb, 0) : bmode == 1 ? desc_kmajor<64>(sb, 0)
+                        : bmode == 2 ? desc_mnmajor<64>(sb, 0, 8192) : desc_mnmajor<128>(sb, 0, 16384);
     // latency of one MMA: issue -> commit -> barrier observed
     long long t0 = clock64();
     mma_ss(tmem, ad, bd, idesc, 0);
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int N, int mode, int nac
     mbar_wait(&bar, 0);
     long long t1 = clock64();
     const uint32_t acc_stride = nacc > 1 ? (uint32_t)N : 0u;
-    if (mode & 1) {
+    if (amode == 1) {
       for (int i = 0; i < count; i += 8) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) mma_ts(tmem + (j & 3) * acc_stride, tmem + 448, bd + (uint64_t)((j & 3) * 2), idesc, 1);
@@ -241,6 +244,63 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int N, int mode, int nac
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+
+// ---- cost of tcgen05.commit in the issue stream: groups of `per_group` MMAs followed by `ncommit` commits ----
+__global__ void __launch_bounds__(128) umma_commit_kernel(int per_group, int ncommit, int groups, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw3[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw3) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bars[4];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, 32, false, false, true, true);
+    const uint64_t ad = desc_kmajor<128>(smem_u32(smem), 0);
+    const uint64_t bd = desc_kmajor<128>(smem_u32(smem) + 32768, 0);
+    long long t0 = clock64();
+    for (int g = 0; g < groups; ++g) {
+      for (int j = 0; j < per_group; ++j) mma_ss(tmem, ad, bd, idesc, 1);
+      for (int c = 0; c < ncommit; ++c) mma_commit(&bars[c]);
+    }
+    long long t1 = clock64();
+    mma_commit(&bars[3]);
+    mbar_wait(&bars[3], 0);
+    long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static void commit_case(int per_group, int ncommit, char* report, size_t cap) {
+  long long* d = nullptr;
+  long long h[2] = {0, 0};
+  const int groups = 256;
+  cudaMalloc(&d, sizeof(h));
+  cudaFuncSetAttribute(umma_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  umma_commit_kernel<<<1, 128, 66560>>>(per_group, ncommit, groups, d);
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    rep(report, cap, "mma-commit/ CUDA-ERROR\n");
+    return;
+  }
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  rep(report, cap, "mma-commit/%d MMAs (N=32) + %d commits per group: issue %7.1f clk/group, complete %7.1f clk/group\n", per_group,
+      ncommit, (double)h[0] / groups, (double)h[1] / groups);
 }
 
 static void rate_case(const char* name, int N, int mode, int nacc, char* report, size_t cap) {
@@ -407,15 +467,27 @@ int umma_selftest(char* report, size_t cap) {
     }
     if (c.cfg.variant == 0) fails += r;  // diagnostic variants do not count
   }
-  rate_case("SS N=128 1 acc", 128, 0, 1, report, cap);
-  rate_case("SS N=256 1 acc", 256, 0, 1, report, cap);
-  rate_case("SS N=64 1 acc", 64, 0, 1, report, cap);
-  rate_case("SS N=32 1 acc", 32, 0, 1, report, cap);
-  rate_case("SS N=32 4 acc", 32, 0, 4, report, cap);
-  rate_case("TS N=32 1 acc", 32, 1, 1, report, cap);
-  rate_case("TS N=32 4 acc", 32, 1, 4, report, cap);
-  rate_case("TS N=64 1 acc", 64, 1, 1, report, cap);
-  rate_case("TS N=128 1 acc", 128, 1, 1, report, cap);
+  // mode = amode | bmode << 2;  amode: 0 smem K-major SW128, 1 TMEM, 2 smem MN-major SW128, 3 smem K-major SW64
+  //                            bmode: 0 K-major SW128, 1 K-major SW64, 2 MN-major SW64, 3 MN-major SW128
+  rate_case("A K128  B K128  N=256", 256, 0 | 0 << 2, 1, report, cap);
+  rate_case("A K128  B K128  N=128", 128, 0 | 0 << 2, 1, report, cap);
+  rate_case("A K128  B K128  N=64", 64, 0 | 0 << 2, 1, report, cap);
+  rate_case("A K128  B K128  N=32", 32, 0 | 0 << 2, 1, report, cap);
+  rate_case("A TMEM  B K128  N=128", 128, 1 | 0 << 2, 1, report, cap);
+  rate_case("A TMEM  B K128  N=32", 32, 1 | 0 << 2, 1, report, cap);
+  rate_case("A K64   B K64   N=128", 128, 3 | 1 << 2, 1, report, cap);
+  rate_case("A TMEM  B K64   N=64", 64, 1 | 1 << 2, 1, report, cap);
+  rate_case("A K128  B MN64  N=32", 32, 0 | 2 << 2, 1, report, cap);
+  rate_case("A TMEM  B MN64  N=32", 32, 1 | 2 << 2, 1, report, cap);
+  rate_case("A K128  B MN128 N=64", 64, 0 | 3 << 2, 1, report, cap);
+  rate_case("A TMEM  B MN128 N=128", 128, 1 | 3 << 2, 1, report, cap);
+  rate_case("A MN128 B MN64  N=32", 32, 2 | 2 << 2, 1, report, cap);
+  rate_case("A MN128 B K128  N=128", 128, 2 | 0 << 2, 1, report, cap);
+  commit_case(8, 0, report, cap);
+  commit_case(8, 1, report, cap);
+  commit_case(8, 3, report, cap);
+  commit_case(4, 1, report, cap);
+  commit_case(2, 2, report, cap);
   mufu_case<0>("tanh.approx.f32", 4, report, cap);
   mufu_case<1>("ex2+rcp f32 (sigmoid)", 2, report, cap);
   mufu_case<2>("tanh.approx.bf16x2", 4, report, cap);
