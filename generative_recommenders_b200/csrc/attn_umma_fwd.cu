@@ -43,7 +43,7 @@ struct FwdCfg {
   static constexpr int NBOX = D / BOX_COLS;
   static constexpr int BOX_BYTES = 128 * SW;
   static constexpr int TILE_BYTES = 128 * D * 2;
-  static constexpr int STAGES = (D <= 64) ? 4 : 3;           // K / V TMA ring depth
+  static constexpr int STAGES = 3;   // K / V TMA rings: stage = score slot = tile % 3 (their release shares the slot barriers)
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + TILE_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * TILE_BYTES;
@@ -61,8 +61,8 @@ struct FwdCfg {
 
 struct FwdBars {
   uint64_t q_full;
-  uint64_t k_full[4], k_empty[4], v_full[4], v_empty[4];
-  uint64_t s_full[3], p_full[3];
+  uint64_t k_full[3], v_full[3];
+  uint64_t s_full[3], p_full[3], pv_done[3];
   uint64_t o_full;
   uint32_t tmem_base;
 };
@@ -96,15 +96,12 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     mbar_init(&bars->q_full, 1);
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&bars->k_full[i], 1);
-      mbar_init(&bars->k_empty[i], 1);
-      mbar_init(&bars->v_full[i], 1);
-      mbar_init(&bars->v_empty[i], 1);
-    }
     for (int i = 0; i < 3; ++i) {
+      mbar_init(&bars->k_full[i], 1);
+      mbar_init(&bars->v_full[i], 1);
       mbar_init(&bars->s_full[i], 1);
       mbar_init(&bars->p_full[i], 128);
+      mbar_init(&bars->pv_done[i], 1);
     }
     mbar_init(&bars->o_full, 1);
     fence_barrier_init();
@@ -126,7 +123,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
         tma_load_3d(sQ + bx * Cfg::BOX_BYTES, &p.tmQ, &bars->q_full, bx * Cfg::BOX_COLS, h, (int)(row0 + m0));
       for (int i = 0; i < T; ++i) {
         const int st = i % NST;
-        if (i >= NST) mbar_wait(&bars->k_empty[st], ((i / NST) - 1) & 1);
+        if (i >= 3) mbar_wait(&bars->s_full[st], ((i / 3) - 1) & 1);  // Q K_{i-3}^T has consumed this stage
 #ifdef HSTU_EXP_NO_KLOAD
         if (i >= NST) {  // ablation experiment only
           mbar_arrive(&bars->k_full[st]);
@@ -146,7 +143,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       prefetch_tensormap(&p.tmV);
       for (int i = 0; i < T; ++i) {
         const int st = i % NST;
-        if (i >= NST) mbar_wait(&bars->v_empty[st], ((i / NST) - 1) & 1);
+        if (i >= 3) mbar_wait(&bars->pv_done[st], ((i / 3) - 1) & 1);  // P_{i-3} V_{i-3} has consumed this stage
 #ifdef HSTU_EXP_NO_VLOAD
         if (i >= NST) {  // ablation experiment only: no TMA traffic for V after the ring has been filled once
           mbar_arrive(&bars->v_full[st]);
@@ -161,57 +158,55 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    // The whole warp runs the (warp-uniform) control flow and one fixed lane issues: descriptor arithmetic then stays in
-    // the uniform datapath.  Descriptors are built once; per MMA only the 14-bit address field moves (one 64-bit add of a
-    // compile-time constant): the single issuing thread is on the critical path of every tile.
+    // ---------------- MMA issuer 1: S_i = Q K_i^T ----------------
+    // Two issuing threads (this warp and warp 2): every tcgen05.mma blocks its issuer ~45 clk and every tcgen05.commit
+    // ~100-200 clk (measured, profiles/r01_umma_selftest.txt), so one thread issuing 10 MMAs + 4 commits per tile was the
+    // critical path of the whole kernel.  The whole warp runs the warp-uniform control flow, one fixed lane issues;
+    // descriptors are built once and only their address field is advanced.  One commit per tile and thread: K / V stages
+    // are released through the slot barriers (stage = slot = tile % 3).
     const bool leader = lane == 0;
     constexpr uint32_t idesc_qk = make_idesc(128, 128, false, false, BF16, BF16);
-    constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, BF16, BF16);
     const uint64_t dq0 = desc_kmajor<SW>(smem_u32(sQ), 0);
     const uint64_t dk0 = desc_kmajor<SW>(smem_u32(sK), 0);
-    const uint64_t dv0 = desc_mnmajor<SW>(smem_u32(sV), 0, Cfg::BOX_BYTES);
-    auto issue_qk = [&](int i) {
-      const int st = i % NST;
-      mbar_wait(&bars->k_full[st], (i / NST) & 1);
+    mbar_wait(&bars->q_full, 0);
+    for (int i = 0; i < T; ++i) {
+      const int st = i % 3;
+      if (i >= 3) mbar_wait(&bars->pv_done[st], ((i / 3) - 1) & 1);  // P_{i-3} (front of this slot) has been consumed
+      mbar_wait(&bars->k_full[st], (i / 3) & 1);
       tc_fence_after_sync();
       const uint64_t kd = dk0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
-      const uint32_t ts = tmem + Cfg::TMEM_S + (i % 3) * 128;
+      const uint32_t ts = tmem + Cfg::TMEM_S + st * 128;
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
-          constexpr int dummy = 0;
           const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
           const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
           mma_ss(ts, dq0 + o, kd + o, idesc_qk, ks > 0);
-          (void)dummy;
         }
-        mma_commit(&bars->k_empty[st]);
-        mma_commit(&bars->s_full[i % 3]);
+        mma_commit(&bars->s_full[st]);
       }
       __syncwarp();
-    };
-    mbar_wait(&bars->q_full, 0);
-    issue_qk(0);
-    if (T > 1) issue_qk(1);
-    if (T > 2) issue_qk(2);
+    }
+  } else if (warp == 2) {
+    // ---------------- MMA issuer 2: O += P_i V_i (A = P from TMEM, B = V read MN-major) ----------------
+    const bool leader = lane == 0;
+    constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, BF16, BF16);
+    const uint64_t dv0 = desc_mnmajor<SW>(smem_u32(sV), 0, Cfg::BOX_BYTES);
     for (int i = 0; i < T; ++i) {
-      const int st = i % NST, slot = i % 3;
-      mbar_wait(&bars->p_full[slot], (i / 3) & 1);   // P_i sits in TMEM (front of score slot i % 3)
-      mbar_wait(&bars->v_full[st], (i / NST) & 1);
+      const int st = i % 3;
+      mbar_wait(&bars->p_full[st], (i / 3) & 1);   // P_i sits in TMEM (front of score slot i % 3)
+      mbar_wait(&bars->v_full[st], (i / 3) & 1);
       tc_fence_after_sync();
       const uint64_t vd = dv0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
-      const uint32_t tp = tmem + Cfg::TMEM_S + slot * 128;
+      const uint32_t tp = tmem + Cfg::TMEM_S + st * 128;
       if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)  // A = P from TMEM (16 bf16 of K per 8 columns), B = V read MN-major
+        for (int ks = 0; ks < 8; ++ks)  // 16 bf16 of K per 8 TMEM columns
           mma_ts(tmem + Cfg::TMEM_O + (ks % Cfg::NACC) * D, tp + ks * 8, vd + (uint64_t)((ks * 16 * SW) >> 4), idesc_pv,
                  (i > 0) || (ks >= Cfg::NACC));
-        mma_commit(&bars->v_empty[st]);
+        mma_commit(&bars->pv_done[st]);
       }
       __syncwarp();
-      // the tensor pipe executes this thread's MMAs in order: Q K_{i+3}^T overwrites slot i % 3 only after P_i V_i has read it
-      if (i + 3 < T) issue_qk(i + 3);
     }
     if (leader) mma_commit(&bars->o_full);
     __syncwarp();
