@@ -52,35 +52,36 @@ struct BwdCfg {
   static constexpr int BOX_BYTES = 128 * SW;
   static constexpr int TILE_BYTES = 128 * D * 2;
   static constexpr int PT_BYTES = 128 * 128 * 2;          // one pair buffer: two [128 kv][64 q] boxes
-  static constexpr int STAGES = (D <= 32) ? 4 : 2;        // Q_i / dO_i TMA ring depth
+  static constexpr int STAGES = 4;                        // Q_i / dO_i TMA ring depth
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + TILE_BYTES;
   static constexpr int OFF_Q = OFF_V + TILE_BYTES;
   static constexpr int OFF_DO = OFF_Q + STAGES * TILE_BYTES;
-  static constexpr int OFF_DST = OFF_DO + STAGES * TILE_BYTES;   // dS^T boxes [kv][q] (tile i -> pair buffer i & 1): A of dK
-  static constexpr int OFF_DS = OFF_DST + 2 * PT_BYTES;          // dS   boxes [q][kv]: A of dQ (K-major; an MN-major A costs ~4x)
-  static constexpr int OFF_BAR = OFF_DS + 2 * PT_BYTES;
+  // dS^T boxes [kv][q] (tile i -> pair buffer i & 1): read K-major as A of dK (M = kv) and MN-major as A of dQ (M = q)
+  static constexpr int OFF_DST = OFF_DO + STAGES * TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_DST + 2 * PT_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   // TMEM: a ring of NSLOT score slots, each {S^T half-tile: 64 columns, dP^T half-tile: 64 columns} (a half-tile is
-  // 128 key rows x 64 query rows; after the elementwise stage the fronts of the two halves hold P^T and dS^T as bf16),
-  // the dV, dK and dQ accumulators, and K and V themselves as A operands (bf16, d/2 columns each).
+  // 128 key rows x 64 query rows; after the elementwise stage the front of the S^T half holds P^T as bf16), the dV and
+  // dK accumulators and TWO dQ accumulators (tile i -> buffer i & 1, so the warpgroups can drain dQ two tiles late and
+  // never wait for it).
   static constexpr int NSLOT = (384 + 4 * D <= 512) ? 3 : 2;
   static constexpr int TMEM_SLOT = 0;
   static constexpr int TMEM_DV = NSLOT * 128;
   static constexpr int TMEM_DK = TMEM_DV + D;
-  static constexpr int TMEM_DQ = TMEM_DK + D;
-  static constexpr int TMEM_K = TMEM_DQ + D;
-  static constexpr int TMEM_V = TMEM_K + D / 2;
-  static_assert(TMEM_V + D / 2 <= 512, "TMEM budget");
+  static constexpr int TMEM_DQ = TMEM_DK + D;   // two buffers of D columns
+  static_assert(TMEM_DQ + 2 * D <= 512, "TMEM budget");
   // scripts/sim_bwd_protocol.py: a 3-slot score ring needs the Q/dO ring to be at least 4 deep (the scores of tile i+2 are
   // requested before tile i releases its stage), otherwise the producer and the MMA issuer wait on each other.
   static_assert(NSLOT == 2 || STAGES >= 4, "3-slot score ring needs >= 4 Q/dO stages");
 };
 
 struct BwdBars {
-  uint64_t kv_full, kvt_ready;
-  uint64_t q_full[4], q_empty[4];
-  uint64_t s_full[3], unit_done[4], pair_empty[2], dq_full, dq_empty, fin_full;
+  uint64_t kv_full;
+  uint64_t q_full[4];
+  uint64_t s_full[3], unit_done[4];
+  uint64_t tile_done[4];  // tile i -> [i % 4]: both issuers have finished every GEMM of query tile i (count 2)
+  uint64_t dq_empty[2], fin_full;
   uint32_t tmem_base;
 };
 
@@ -130,22 +131,18 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
   uint8_t* sQ = smem + Cfg::OFF_Q;
   uint8_t* sDO = smem + Cfg::OFF_DO;
   uint8_t* sDST = smem + Cfg::OFF_DST;
-  uint8_t* sDS = smem + Cfg::OFF_DS;
   BwdBars* bars = reinterpret_cast<BwdBars*>(smem + Cfg::OFF_BAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     mbar_init(&bars->kv_full, 1);
-    mbar_init(&bars->kvt_ready, 256);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->q_full[i], 1);
-      mbar_init(&bars->q_empty[i], 2);  // both MMA issuers release a Q/dO stage
+      mbar_init(&bars->tile_done[i], 2);
     }
     for (int i = 0; i < 3; ++i) mbar_init(&bars->s_full[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bars->unit_done[i], 128);
-    for (int i = 0; i < 2; ++i) mbar_init(&bars->pair_empty[i], 1);
-    mbar_init(&bars->dq_full, 1);
-    mbar_init(&bars->dq_empty, 256);
+    for (int i = 0; i < 2; ++i) mbar_init(&bars->dq_empty[i], 256);
     mbar_init(&bars->fin_full, 2);     // both MMA issuers
     fence_barrier_init();
   }
@@ -170,7 +167,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       }
       for (int i = 0; i < T; ++i) {
         const int st = i % NST;
-        if (i >= NST) mbar_wait(&bars->q_empty[st], ((i / NST) - 1) & 1);
+        if (i >= NST) mbar_wait(&bars->tile_done[(i - NST) & 3], ((i - NST) >> 2) & 1);  // tile i - NST is done with this stage
         mbar_arrive_expect_tx(&bars->q_full[st], 2 * Cfg::TILE_BYTES);
         const int qrow = (int)(row0 + (long long)q_tile(i) * 128);
 #pragma unroll
@@ -190,6 +187,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     const bool leader = lane == 0;
     constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, BF16, BF16);    // S^T, dP^T half-tiles
     constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dV: A = P^T (TMEM), B MN-major
+    const uint64_t dk_k = desc_kmajor<SW>(smem_u32(sK), 0);                        // K as K-major A (S^T)
+    const uint64_t dv_k = desc_kmajor<SW>(smem_u32(sV), 0);                        // V as K-major A (dP^T)
     const uint64_t dq_k = desc_kmajor<SW>(smem_u32(sQ), 0);                        // Q_i rows as K-major B
     const uint64_t ddo_k = desc_kmajor<SW>(smem_u32(sDO), 0);                      // dO_i rows as K-major B
     const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
@@ -205,12 +204,12 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
           mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (up > 0) || (ks > 0));
-        if (hp == 1) mma_commit(&bars->q_empty[stp]);  // this issuer is done with stage stp (scores and dV of both halves)
+        if (hp == 1) mma_commit(&bars->tile_done[ip & 3]);  // this issuer's GEMMs of tile ip (scores, dV) are all issued
       }
       __syncwarp();
     };
     // ---- issuer X (this warp): the score GEMMs S^T, dP^T of every unit, as soon as their TMEM slot is free ----
-    mbar_wait(&bars->kvt_ready, 0);  // K and V have been copied into TMEM by the warpgroups
+    mbar_wait(&bars->kv_full, 0);
     tc_fence_after_sync();
     for (int u = 0; u < U; ++u) {
       const int i = u >> 1, hf = u & 1, st = i % NST, slot = u % NSLOT;
@@ -231,13 +230,13 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         for (int ks = 0; ks < D / 16; ++ks) {
           const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
           const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
-          mma_ts(ts, tmem + Cfg::TMEM_K + ks * 8, dq_k + row_off + o, idesc_s, ks > 0);       // A = K from TMEM
+          mma_ss(ts, dk_k + o, dq_k + row_off + o, idesc_s, ks > 0);
         }
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
           const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
           const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
-          mma_ts(ts + 64, tmem + Cfg::TMEM_V + ks * 8, ddo_k + row_off + o, idesc_s, ks > 0);  // A = V from TMEM
+          mma_ss(ts + 64, dv_k + o, ddo_k + row_off + o, idesc_s, ks > 0);
         }
         mma_commit(&bars->s_full[slot]);
         HSTU_TSTAMP(0, u, 2);
@@ -253,9 +252,10 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     constexpr int NSLOT = Cfg::NSLOT;
     (void)NSLOT;
     const bool leader = lane == 0;
-    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dK, dQ: A K-major, B MN-major
+    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dK: A K-major, B MN-major
+    constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // dQ: A MN-major, B MN-major
     const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box [kv][q] as K-major A (dK)
-    const uint64_t dsq_k = desc_kmajor<128>(smem_u32(sDS), 0);                     // dS boxes [q][kv] as K-major A (dQ)
+    const uint64_t dds_mn = desc_mnmajor<128>(smem_u32(sDST), 0, 16384);           // the box pair as MN-major A (dQ)
     const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
     const uint64_t dk_mn = desc_mnmajor<SW>(smem_u32(sK), 0, Cfg::BOX_BYTES);      // K as MN-major B (dQ)
     const int U = 2 * T;
@@ -279,20 +279,18 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       if (leader) HSTU_TSTAMP(1, u, 2);
       __syncwarp();
       if (hf == 1) {
-        if (i >= 1) {
-          mbar_wait(&bars->dq_empty, (i - 1) & 1);  // dQ_{i-1} has been drained from TMEM
+        if (i >= 2) {
+          mbar_wait(&bars->dq_empty[i & 1], ((i >> 1) - 1) & 1);  // dQ_{i-2} has been drained from this accumulator
           tc_fence_after_sync();
         }
         if (leader) {
           HSTU_TSTAMP(1, u, 3);
-          const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);  // the dS boxes of this query tile in shared memory
+          const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);  // the dS^T boxes of this query tile
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows: box ks / 4 holds keys [64 (ks/4), +64), 32 bytes per k-step
-            mma_ss(tmem + Cfg::TMEM_DQ, dsq_k + pair + (uint64_t)(((ks >> 2) * 16384 + (ks & 3) * 32) >> 4),
-                   dk_mn + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, ks > 0);
-          mma_commit(&bars->q_empty[st]);
-          mma_commit(&bars->pair_empty[pb]);
-          mma_commit(&bars->dq_full);
+          for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows, 16 per step; M = the 128 query rows = both boxes of the pair
+            mma_ss(tmem + Cfg::TMEM_DQ + (i & 1) * D, dds_mn + pair + (uint64_t)((ks * 16 * 128) >> 4),
+                   dk_mn + (uint64_t)((ks * 16 * SW) >> 4), idesc_dq, ks > 0);
+          mma_commit(&bars->tile_done[i & 3]);  // one commit: dK of both halves and dQ_i (tcgen05.commit costs ~150 clk)
         }
         __syncwarp();
       }
@@ -306,45 +304,24 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     const int row = quad * 32 + lane;              // key row inside the tile == TMEM lane
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
     const int j_pos = n0 + row;
-    const float ah = p.alpha_half;
+    const float2 ah2 = make_float2(p.alpha_half, p.alpha_half);
+    const float2 half2v = make_float2(0.5f, 0.5f), nhalf2v = make_float2(-0.5f, -0.5f);
     const bool fast = msk.fast != 0;
     const bool j_ok = j_pos < len;
     const bool j_hist = j_ok && (!msk.has_tgt || j_pos < msk.max_id);  // fast mask: valid = (j_hist & i > j) | (i == j)
     const int cbase = wg * 64;
     const int qcol0 = wg * (D / 2);                // dQ columns drained by this warpgroup
 
-    {
-      // K (warpgroup 0) / V (warpgroup 1) -> TMEM as bf16 A operands: row r of the tile = TMEM lane r, 16 elements per 8 columns
-      mbar_wait(&bars->kv_full, 0);
-      const uint8_t* src = (wg == 0 ? sK : sV);
-      const uint32_t dst = tmem + (wg == 0 ? Cfg::TMEM_K : Cfg::TMEM_V) + lane_bits;
-#pragma unroll
-      for (int c = 0; c < D / 32; ++c) {  // 32 elements = 64 bytes = 4 swizzled 16-byte chunks = 16 TMEM columns
-        uint32_t r[16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int chunk = c * 4 + j;                        // 16-byte chunk index along the row
-          const int bx = chunk / (SW / 16), cc = chunk % (SW / 16);
-          const uint4 v = *reinterpret_cast<const uint4*>(src + bx * Cfg::BOX_BYTES + swizzled_chunk_offset<SW>(row, cc));
-          r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
-        }
-        tmem_st16(dst + c * 16, r);
-      }
-      tmem_st_wait();
-      tc_fence_before_sync();
-      mbar_arrive(&bars->kvt_ready);
-    }
-
     auto drain_dq = [&](int i) {
       // dQ tile of query tile i: TMEM lane = query row -> fp32 vector reductions into dq_acc
-      mbar_wait(&bars->dq_full, i & 1);
+      mbar_wait(&bars->tile_done[i & 3], (i >> 2) & 1);
       tc_fence_after_sync();
       const int qpos = q_tile(i) * 128 + row;
       float* dst = p.dq_acc + ((row0 + qpos) * p.heads + h) * (long long)D + qcol0;
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
         uint32_t r[16];
-        tmem_ld16(tmem + Cfg::TMEM_DQ + qcol0 + c * 16 + lane_bits, r);
+        tmem_ld16(tmem + Cfg::TMEM_DQ + (i & 1) * D + qcol0 + c * 16 + lane_bits, r);
         tmem_ld_wait();
 #ifdef HSTU_EXP_NO_DQ_RED
         if (qpos < -1) {
@@ -358,7 +335,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         }
       }
       tc_fence_before_sync();
-      mbar_arrive(&bars->dq_empty);
+      mbar_arrive(&bars->dq_empty[i & 1]);
     };
 
     for (int i = 0; i < T; ++i) {
@@ -372,16 +349,13 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       const int mh0 = m0 + cbase;                   // first query row of the half
       const bool full = fast && (mh0 >= n0 + 128) && (mh0 + 64 <= len) && (!msk.has_tgt || n0 + 128 <= msk.max_id);
       const int mode = full ? 0 : (fast ? 1 : 2);
-      // dS box of this key row: keys [0,64) -> box 0, [64,128) -> box 1; 16-byte chunk (row % 64) / 8, 2 bytes at (row % 8) * 2
-      const uint32_t sDSw = smem_u32(sDS + (i & 1) * Cfg::PT_BYTES + (row >> 6) * 16384) + (row & 7) * 2;
-      const uint32_t ds_chunk = (uint32_t)((row & 63) >> 3);
       const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + wg * 16384);
       const int jr = j_pos - m0 - cbase;           // query column (relative to this warpgroup's block) equal to j
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
       const uint32_t st_addr = tmem + Cfg::TMEM_SLOT + slot * 128 + lane_bits;
       const uint32_t dp_addr = st_addr + 64;
 #ifdef HSTU_EXP_NO_ELEM
-      if (i >= 2) mbar_wait(&bars->pair_empty[i & 1], ((i >> 1) - 1) & 1);  // keep the protocol intact
+      if (i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // keep the protocol intact
 #endif
 #pragma unroll
 #ifdef HSTU_EXP_NO_ELEM
@@ -395,21 +369,23 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
         tmem_ld_wait();
         uint32_t pp[16], dd[16];
         // p = x sig(x) and g = sig (1 + x (1 - sig)) from one tanh: x = 2 hh, sig = (1 + t) / 2
-#define HSTU_BWD_ELEM(E, PV, DV)                                   \
-  {                                                                \
-    const float hh = __uint_as_float(s[E]) * ah;                   \
-    const float t = tanh_approx(hh);                               \
-    PV = fmaf(hh, t, hh);                                          \
-    const float sig = fmaf(0.5f, t, 0.5f);                         \
-    const float onem = fmaf(-0.5f, t, 0.5f);                       \
-    DV = __uint_as_float(dp[E]) * fmaf(PV, onem, sig);             \
+        // packed fp32x2 arithmetic (FMUL2 / FFMA2): two elements per issued instruction, one MUFU.TANH per element
+#define HSTU_BWD_ELEM2(E, P0, P1, D0, D1)                                                                      \
+  {                                                                                                            \
+    const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[E]), __uint_as_float(s[E + 1])), ah2);          \
+    const float2 t = make_float2(tanh_approx(hh.x), tanh_approx(hh.y));                                        \
+    const float2 pv = __ffma2_rn(hh, t, hh);                                                                   \
+    const float2 sig = __ffma2_rn(half2v, t, half2v);                                                          \
+    const float2 onem = __ffma2_rn(nhalf2v, t, half2v);                                                        \
+    const float2 dv = __fmul2_rn(make_float2(__uint_as_float(dp[E]), __uint_as_float(dp[E + 1])),              \
+                                 __ffma2_rn(pv, onem, sig));                                                   \
+    P0 = pv.x; P1 = pv.y; D0 = dv.x; D1 = dv.y;                                                                \
   }
         if (mode == 0) {
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             float p0, p1, d0, d1;
-            HSTU_BWD_ELEM(e, p0, d0);
-            HSTU_BWD_ELEM(e + 1, p1, d1);
+            HSTU_BWD_ELEM2(e, p0, p1, d0, d1);
             pp[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
             dd[e >> 1] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
           }
@@ -420,8 +396,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             float p0, p1, d0, d1;
-            HSTU_BWD_ELEM(e, p0, d0);
-            HSTU_BWD_ELEM(e + 1, p1, d1);
+            HSTU_BWD_ELEM2(e, p0, p1, d0, d1);
             const int c0 = c * 32 + e;
             const bool v0 = ((c0 > lo_c) | (c0 == dg_c)) & (c0 < len_rel);
             const bool v1 = ((c0 + 1 > lo_c) | (c0 + 1 == dg_c)) & (c0 + 1 < len_rel);
@@ -434,8 +409,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             float p0, p1, d0, d1;
-            HSTU_BWD_ELEM(e, p0, d0);
-            HSTU_BWD_ELEM(e + 1, p1, d1);
+            HSTU_BWD_ELEM2(e, p0, p1, d0, d1);
             const int i_pos = m0 + cbase + c * 32 + e;
             const bool v0 = j_ok && i_pos < len && mask_valid(msk, i_pos, j_pos);
             const bool v1 = j_ok && i_pos + 1 < len && mask_valid(msk, i_pos + 1, j_pos);
@@ -445,29 +419,24 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
             dd[e >> 1] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
           }
         }
-#undef HSTU_BWD_ELEM
-        if (c == 0 && i >= 2) mbar_wait(&bars->pair_empty[i & 1], ((i >> 1) - 1) & 1);  // GEMMs of tile i-2 are done with this buffer pair
+#undef HSTU_BWD_ELEM2
+        if (c == 0 && i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
         // P^T chunk c (32 bf16 = 16 columns) overwrites the already-read front of the S^T half of the slot: A of the dV GEMM
         tmem_st16(st_addr + c * 16, pp);
-        // dS^T [kv][q] (16-byte stores, A of dK) and dS [q][kv] (2-byte stores, A of dQ)
+        // dS^T [kv][q] (16-byte stores): A of dK as stored, A of dQ read MN-major
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4)
           st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + j4), dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const uint32_t qrow = (uint32_t)(cbase + c * 32 + e);                  // query row of the 128-row tile
-          const uint32_t a = sDSw + qrow * 128 + ((ds_chunk ^ (qrow & 7)) << 4);
-          st_shared_b16(a, (e & 1) ? (dd[e >> 1] >> 16) : dd[e >> 1]);
-        }
       }
       tmem_st_wait();
       tc_fence_before_sync();
       fence_proxy_async_smem();
       if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 2);
       mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);
-      if (i >= 1) drain_dq(i - 1);
+      if (i >= 2) drain_dq(i - 2);  // two tiles late: dQ_{i-2} finished long ago, no stall
       if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 3);
     }
+    if (T >= 2) drain_dq(T - 2);
     drain_dq(T - 1);
     // ---------------- epilogue: dV (warpgroup 0) / dK (warpgroup 1): TMEM -> scale -> global ----------------
     mbar_wait(&bars->fin_full, 0);
