@@ -29,7 +29,7 @@ using namespace umma;
 bool umma_fwd_supported(const hstu_attn_params& p);
 
 struct alignas(64) BwdParams {
-  CUtensorMap tmQ, tmK, tmV, tmDO;
+  CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;  // tmDQ: the fp32 dQ accumulator (TMA reduce-add destination)
   const void* seq_offsets;
   const void* num_targets;
   void* dk;
@@ -52,14 +52,17 @@ struct BwdCfg {
   static constexpr int BOX_BYTES = 128 * SW;
   static constexpr int TILE_BYTES = 128 * D * 2;
   static constexpr int PT_BYTES = 128 * 128 * 2;          // one pair buffer: two [128 kv][64 q] boxes
-  static constexpr int STAGES = 4;                        // Q_i / dO_i TMA ring depth
+  static constexpr int STAGES = (D <= 32) ? 4 : 3;        // Q_i / dO_i TMA ring depth (d = 64: shared memory is full)
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + TILE_BYTES;
   static constexpr int OFF_Q = OFF_V + TILE_BYTES;
   static constexpr int OFF_DO = OFF_Q + STAGES * TILE_BYTES;
   // dS^T boxes [kv][q] (tile i -> pair buffer i & 1): read K-major as A of dK (M = kv) and MN-major as A of dQ (M = q)
   static constexpr int OFF_DST = OFF_DO + STAGES * TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_DST + 2 * PT_BYTES;
+  static constexpr int DQS_BYTES = 128 * D * 2;                  // per warpgroup: 128 query rows x D/2 fp32 columns
+  static constexpr int OFF_DQS = OFF_DST + 2 * PT_BYTES;         // dQ staging boxes (source of the TMA reduce-add)
+  static constexpr int OFF_BAR = OFF_DQS + 2 * DQS_BYTES;
+  static_assert(OFF_BAR + 256 + 1024 <= 232448, "shared memory budget");
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   // TMEM: a ring of NSLOT score slots, each {S^T half-tile: 64 columns, dP^T half-tile: 64 columns} (a half-tile is
   // 128 key rows x 64 query rows; after the elementwise stage the front of the S^T half holds P^T as bf16), the dV and
@@ -81,6 +84,7 @@ struct BwdBars {
   uint64_t q_full[4];
   uint64_t s_full[3], unit_done[4];
   uint64_t tile_done[4];  // tile i -> [i % 4]: both issuers have finished every GEMM of query tile i (count 2)
+  uint64_t slot_free[3];  // unit u -> [u % NSLOT]: dV of the unit has consumed P^T in the slot
   uint64_t dq_empty[2], fin_full;
   uint32_t tmem_base;
 };
@@ -131,6 +135,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
   uint8_t* sQ = smem + Cfg::OFF_Q;
   uint8_t* sDO = smem + Cfg::OFF_DO;
   uint8_t* sDST = smem + Cfg::OFF_DST;
+  uint8_t* sDQS = smem + Cfg::OFF_DQS;
   BwdBars* bars = reinterpret_cast<BwdBars*>(smem + Cfg::OFF_BAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -143,7 +148,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     for (int i = 0; i < 3; ++i) mbar_init(&bars->s_full[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bars->unit_done[i], 128);
     for (int i = 0; i < 2; ++i) mbar_init(&bars->dq_empty[i], 256);
-    mbar_init(&bars->fin_full, 2);     // both MMA issuers
+    mbar_init(&bars->fin_full, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&bars->slot_free[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
@@ -178,45 +184,31 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
+    // ---------------- MMA issuers: warps 1, 2, 3 ----------------
     // Work is pipelined in "units" u = 2 i + h: half h (64 query rows) of query tile i.  Unit u's scores live in TMEM
-    // slot u % NSLOT; warpgroup h turns them into the P^T / dS^T box (pair i & 1, box h) in shared memory.
-    // The whole warp runs the warp-uniform control flow, one fixed lane issues; descriptors are built once and only
-    // their address field is advanced (the issuing thread is on the critical path: ~32 MMAs per query tile).
+    // slot u % NSLOT; warpgroup h turns them into P^T (bf16, over the front of the slot) and the dS^T box (pair i & 1,
+    // box h) in shared memory.  Three threads issue, each with its own wait -> issue -> commit loop: measured
+    // (umma_selftest mma-multi), one thread that commits after 8 MMAs reaches 71 clk / MMA, two or three threads 40,
+    // because tcgen05.commit and the barrier waits stall only their own issuer.
+    //   X (this warp): S^T, dP^T of every unit.     Y (warp 2): dV, dK of every unit.     Z (warp 3): dQ of every tile.
+    // The whole warp runs the warp-uniform control flow, one fixed lane issues; descriptors are built once.
     constexpr int NSLOT = Cfg::NSLOT;
     const bool leader = lane == 0;
     constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, BF16, BF16);    // S^T, dP^T half-tiles
-    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dV: A = P^T (TMEM), B MN-major
     const uint64_t dk_k = desc_kmajor<SW>(smem_u32(sK), 0);                        // K as K-major A (S^T)
     const uint64_t dv_k = desc_kmajor<SW>(smem_u32(sV), 0);                        // V as K-major A (dP^T)
     const uint64_t dq_k = desc_kmajor<SW>(smem_u32(sQ), 0);                        // Q_i rows as K-major B
     const uint64_t ddo_k = desc_kmajor<SW>(smem_u32(sDO), 0);                      // dO_i rows as K-major B
-    const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
     const int U = 2 * T;
-    // dV += P^T dO for unit up: A = P^T from the front of the unit's TMEM slot (written by the warpgroup over S^T)
-    auto issue_dv = [&](int up) {
-      const int ip = up >> 1, hp = up & 1, stp = ip % NST;
-      mbar_wait(&bars->unit_done[hp * 2 + (ip & 1)], (ip >> 1) & 1);
-      tc_fence_after_sync();
-      const uint64_t rows = (uint64_t)((stp * Cfg::TILE_BYTES + hp * 64 * SW) >> 4);
-      const uint32_t tp = tmem + Cfg::TMEM_SLOT + (up % NSLOT) * 128;
-      if (leader) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
-          mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (up > 0) || (ks > 0));
-        if (hp == 1) mma_commit(&bars->tile_done[ip & 3]);  // this issuer's GEMMs of tile ip (scores, dV) are all issued
-      }
-      __syncwarp();
-    };
-    // ---- issuer X (this warp): the score GEMMs S^T, dP^T of every unit, as soon as their TMEM slot is free ----
     mbar_wait(&bars->kv_full, 0);
     tc_fence_after_sync();
     for (int u = 0; u < U; ++u) {
       const int i = u >> 1, hf = u & 1, st = i % NST, slot = u % NSLOT;
       if (leader) HSTU_TSTAMP(0, u, 0);
-      // the slot still holds P^T of unit u - NSLOT: consume it (dV) first; the in-order tensor pipe then lets the new
-      // scores overwrite it
-      if (u >= NSLOT) issue_dv(u - NSLOT);
+      if (u >= NSLOT) {  // the slot still holds P^T of unit u - NSLOT until its dV GEMM has completed
+        mbar_wait(&bars->slot_free[slot], (u / NSLOT - 1) & 1);
+        tc_fence_after_sync();
+      }
       if (hf == 0) {
         mbar_wait(&bars->q_full[st], (i / NST) & 1);
         tc_fence_after_sync();
@@ -243,60 +235,68 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       }
       __syncwarp();
     }
-    for (int up = (U > NSLOT ? U - NSLOT : 0); up < U; ++up) issue_dv(up);
-    if (leader) mma_commit(&bars->fin_full);
-    __syncwarp();
   } else if (warp == 2) {
-    // ---- issuer Y: the gradient GEMMs dV, dK (per unit) and dQ (per query tile).  A second issuing thread keeps the
-    // tensor pipe fed while issuer X sits in a barrier wait (each tcgen05.mma blocks its issuer ~45 clk; measured). ----
+    // ---- issuer Y: dV += P^T dO (A = P^T from the unit's TMEM slot) and dK += dS^T Q (A = the dS^T box) of every unit ----
     constexpr int NSLOT = Cfg::NSLOT;
-    (void)NSLOT;
     const bool leader = lane == 0;
-    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // dK: A K-major, B MN-major
-    constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // dQ: A MN-major, B MN-major
+    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // A K-major, B MN-major
     const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box [kv][q] as K-major A (dK)
-    const uint64_t dds_mn = desc_mnmajor<128>(smem_u32(sDST), 0, 16384);           // the box pair as MN-major A (dQ)
     const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
-    const uint64_t dk_mn = desc_mnmajor<SW>(smem_u32(sK), 0, Cfg::BOX_BYTES);      // K as MN-major B (dQ)
+    const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
     const int U = 2 * T;
     for (int u = 0; u < U; ++u) {
-      const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1;
-      // box (pb, hf) of P^T / dS^T is written.  One barrier per (half, tile parity): with a 3-slot score ring a warpgroup
-      // may finish TWO units before this thread gets here; a single barrier per half would then be two phases ahead and
-      // the parity wait would alias.
+      const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1, slot = u % NSLOT;
+      // P^T / dS^T of the unit are written.  One barrier per (half, tile parity): with a 3-slot score ring a warpgroup may
+      // finish TWO units before this thread gets here; a single barrier per half would then be two phases ahead and the
+      // parity wait would alias.
       if (leader) HSTU_TSTAMP(1, u, 0);
       mbar_wait(&bars->unit_done[hf * 2 + pb], (i >> 1) & 1);
       tc_fence_after_sync();
       if (leader) HSTU_TSTAMP(1, u, 1);
       const uint64_t box = (uint64_t)((pb * Cfg::PT_BYTES + hf * 16384) >> 4);
       const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);  // MN-major B: K rows = the 64 query rows
+      const uint32_t tp = tmem + Cfg::TMEM_SLOT + slot * 128;
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
+          mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (u > 0) || (ks > 0));
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
           mma_ss(tmem + Cfg::TMEM_DK, dds_k + box + (uint64_t)((ks * 32) >> 4), dq_mn + rows + (uint64_t)((ks * 16 * SW) >> 4),
                  idesc_kv, (u > 0) || (ks > 0));
+        mma_commit(&bars->slot_free[slot]);                // the score issuer may overwrite the slot
+        if (hf == 1) mma_commit(&bars->tile_done[i & 3]);  // this issuer is done with Q_i / dO_i and the dS^T boxes of tile i
+        HSTU_TSTAMP(1, u, 2);
       }
-      if (leader) HSTU_TSTAMP(1, u, 2);
       __syncwarp();
-      if (hf == 1) {
-        if (i >= 2) {
-          mbar_wait(&bars->dq_empty[i & 1], ((i >> 1) - 1) & 1);  // dQ_{i-2} has been drained from this accumulator
-          tc_fence_after_sync();
-        }
-        if (leader) {
-          HSTU_TSTAMP(1, u, 3);
-          const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);  // the dS^T boxes of this query tile
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows, 16 per step; M = the 128 query rows = both boxes of the pair
-            mma_ss(tmem + Cfg::TMEM_DQ + (i & 1) * D, dds_mn + pair + (uint64_t)((ks * 16 * 128) >> 4),
-                   dk_mn + (uint64_t)((ks * 16 * SW) >> 4), idesc_dq, ks > 0);
-          mma_commit(&bars->tile_done[i & 3]);  // one commit: dK of both halves and dQ_i (tcgen05.commit costs ~150 clk)
-        }
-        __syncwarp();
-      }
     }
     if (leader) mma_commit(&bars->fin_full);
     __syncwarp();
+  } else if (warp == 3) {
+    // ---- issuer Z: dQ_i = dS_i K (A = the dS^T box pair read MN-major, M = 128 query rows) of every query tile ----
+    const bool leader = lane == 0;
+    constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // A MN-major, B MN-major
+    const uint64_t dds_mn = desc_mnmajor<128>(smem_u32(sDST), 0, 16384);           // the box pair as MN-major A
+    const uint64_t dk_mn = desc_mnmajor<SW>(smem_u32(sK), 0, Cfg::BOX_BYTES);      // K as MN-major B
+    for (int i = 0; i < T; ++i) {
+      const int pb = i & 1;
+      if (leader) HSTU_TSTAMP(4, i, 0);
+      mbar_wait(&bars->unit_done[0 * 2 + pb], (i >> 1) & 1);
+      mbar_wait(&bars->unit_done[1 * 2 + pb], (i >> 1) & 1);
+      if (i >= 2) mbar_wait(&bars->dq_empty[i & 1], ((i >> 1) - 1) & 1);  // dQ_{i-2} has been drained from this accumulator
+      tc_fence_after_sync();
+      if (leader) {
+        HSTU_TSTAMP(4, i, 1);
+        const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);  // the dS^T boxes of this query tile
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows, 16 per step
+          mma_ss(tmem + Cfg::TMEM_DQ + (i & 1) * D, dds_mn + pair + (uint64_t)((ks * 16 * 128) >> 4),
+                 dk_mn + (uint64_t)((ks * 16 * SW) >> 4), idesc_dq, ks > 0);
+        mma_commit(&bars->tile_done[i & 3]);
+        HSTU_TSTAMP(4, i, 2);
+      }
+      __syncwarp();
+    }
   } else if (warp >= 4) {
     // ---------------- elementwise warpgroups ----------------
     const int wg = (warp - 4) >> 2;                // owns query columns [64*wg, 64*wg + 64) of every tile
@@ -312,30 +312,36 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     const int cbase = wg * 64;
     const int qcol0 = wg * (D / 2);                // dQ columns drained by this warpgroup
 
+    // dQ tile of query tile i: TMEM (lane = query row) -> swizzled fp32 staging box in shared memory -> ONE TMA reduce-add
+    // per warpgroup into dq_acc.  (Per-thread red.global.add.v4 cost one L1 wavefront per lane: 1024 per tile, ~40% of the
+    // L1 data pipe that the tensor core's operand fetches also go through; measured with ncu.)
+    const uint32_t sDQSw = smem_u32(sDQS + wg * Cfg::DQS_BYTES);
+    const bool dq_issuer = quad == 0 && lane == 0;
     auto drain_dq = [&](int i) {
-      // dQ tile of query tile i: TMEM lane = query row -> fp32 vector reductions into dq_acc
       mbar_wait(&bars->tile_done[i & 3], (i >> 2) & 1);
       tc_fence_after_sync();
+      if (dq_issuer) bulk_wait_group_read0();      // the previous reduce has finished reading the staging box
+      named_bar_sync(1 + wg, 128);
       const int qpos = q_tile(i) * 128 + row;
-      float* dst = p.dq_acc + ((row0 + qpos) * p.heads + h) * (long long)D + qcol0;
+      const bool q_ok = qpos < len;                // rows past the end of this sequence belong to the next one: add zeros
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
         uint32_t r[16];
         tmem_ld16(tmem + Cfg::TMEM_DQ + (i & 1) * D + qcol0 + c * 16 + lane_bits, r);
         tmem_ld_wait();
-#ifdef HSTU_EXP_NO_DQ_RED
-        if (qpos < -1) {
-#else
-        if (qpos < len) {
-#endif
 #pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            red_add_v4(dst + c * 16 + e, __uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]),
-                       __uint_as_float(r[e + 3]));
-        }
+        for (int e = 0; e < 16; e += 4)
+          st_shared_v4(sDQSw + swizzled_chunk_offset<SW>(row, c * 4 + (e >> 2)), q_ok ? r[e] : 0u, q_ok ? r[e + 1] : 0u,
+                       q_ok ? r[e + 2] : 0u, q_ok ? r[e + 3] : 0u);
       }
       tc_fence_before_sync();
       mbar_arrive(&bars->dq_empty[i & 1]);
+      fence_proxy_async_smem();
+      named_bar_sync(1 + wg, 128);
+      if (dq_issuer) {
+        tma_reduce_add_3d(&p.tmDQ, sDQSw, qcol0, h, (int)(row0 + q_tile(i) * 128));
+        bulk_commit_group();
+      }
     };
 
     for (int i = 0; i < T; ++i) {
@@ -438,6 +444,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     }
     if (T >= 2) drain_dq(T - 2);
     drain_dq(T - 1);
+    if (dq_issuer) bulk_wait_group_read0();      // shared memory must stay valid until the last reduce has read it
     // ---------------- epilogue: dV (warpgroup 0) / dK (warpgroup 1): TMEM -> scale -> global ----------------
     mbar_wait(&bars->fin_full, 0);
     tc_fence_after_sync();
@@ -535,6 +542,7 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   if (int e = make_tmap_rows_heads(&bp.tmK, p.k, p.total_rows, p.heads, D, p.k_row_stride, p.k_head_stride, Cfg::BOX_COLS, 128)) return e;
   if (int e = make_tmap_rows_heads(&bp.tmV, p.v, p.total_rows, p.heads, D, p.v_row_stride, p.v_head_stride, Cfg::BOX_COLS, 128)) return e;
   if (int e = make_tmap_rows_heads(&bp.tmDO, p.dout, p.total_rows, p.heads, D, p.do_row_stride, p.do_head_stride, Cfg::BOX_COLS, 128)) return e;
+  if (int e = make_tmap_rows_heads_f32(&bp.tmDQ, p.workspace, p.total_rows, p.heads, D, D / 2, 128)) return e;
   bp.seq_offsets = p.seq_offsets;
   bp.num_targets = p.num_targets;
   bp.dk = p.dk;
@@ -560,7 +568,7 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   dim3 grid((p.max_seq_len + 127) / 128, p.heads, p.batch);
 #ifdef HSTU_TRACE
   long long* tbuf = nullptr;
-  const size_t tbytes = sizeof(long long) * 4 * 256 * 4;
+  const size_t tbytes = sizeof(long long) * 5 * 256 * 4;
   cudaMalloc(&tbuf, tbytes);
   cudaMemset(tbuf, 0, tbytes);
   cudaMemcpyToSymbol(g_trace, &tbuf, sizeof(tbuf));
@@ -570,11 +578,11 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
 #ifdef HSTU_TRACE
   {
     cudaDeviceSynchronize();
-    static long long host[4 * 256 * 4];
+    static long long host[5 * 256 * 4];
     cudaMemcpy(host, tbuf, tbytes, cudaMemcpyDeviceToHost);
     FILE* f = fopen("gpurun_out/bwd_trace.txt", "w");
     if (f) {
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < 5; ++r)
         for (int i = 0; i < 256; ++i) {
           const long long* e = host + (r * 256 + i) * 4;
           if (e[0] || e[1] || e[2] || e[3]) fprintf(f, "%d %d %lld %lld %lld %lld\n", r, i, e[0], e[1], e[2], e[3]);

@@ -106,6 +106,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// TMA reduce-add of a shared-memory box into global memory (fp32 add done by the L2 / TMA unit; bulk-group completion)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMEM allocation (one full warp executes these)
 // ---------------------------------------------------------------------------------------------
@@ -280,6 +292,7 @@ __device__ __forceinline__ uint32_t swizzled_chunk_offset(uint32_t row, uint32_t
 // ---------------------------------------------------------------------------------------------
 // 3-D map over a [rows, heads, d] bf16/fp16 tensor with arbitrary row / head strides (elements): dims (d, heads, rows),
 // box (box_cols, 1, box_rows), swizzle = box_cols * 2 bytes (32/64/128).  Returns 0 on success.
+int make_tmap_rows_heads_f32(CUtensorMap* out, const void* base, long long rows, int heads, int d, int box_cols, int box_rows);
 int make_tmap_rows_heads(CUtensorMap* out, const void* base, long long rows, int heads, int d, long long row_stride,
                          long long head_stride, int box_cols, int box_rows);
 

@@ -321,6 +321,74 @@ static void rate_case(const char* name, int N, int mode, int nacc, char* report,
       h[0], count, (double)h[1] / count, (double)h[2] / count);
 }
 
+
+// ---- several issuing threads sharing the tensor pipe: `nissuers` warps each issue `groups` x (8 MMAs N=32 + 1 commit), optionally
+// waiting for their own commit before the next group (a dependent hand-off).  Reports aggregate clocks per MMA. ----
+__global__ void __launch_bounds__(128) umma_multi_kernel(int nissuers, int groups, int wait_each, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw4[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw4) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bars[8];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ long long t_begin[4], t_end[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (warp < nissuers && lane == 0) {
+    const uint32_t idesc = make_idesc(128, 32, false, false, true, true);
+    const uint64_t ad = desc_kmajor<128>(smem_u32(smem) + warp * 4096, 0);
+    const uint64_t bd = desc_kmajor<128>(smem_u32(smem) + 32768 + warp * 4096, 0);
+    const uint32_t acc = tmem + warp * 64;
+    t_begin[warp] = clock64();
+    for (int g = 0; g < groups; ++g) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mma_ss(acc, ad + (uint64_t)((j & 3) * 2), bd + (uint64_t)((j & 3) * 2), idesc, 1);
+      mma_commit(&bars[warp]);
+      if (wait_each) mbar_wait(&bars[warp], g & 1);
+    }
+    mma_commit(&bars[4 + warp]);   // final drain on a fresh barrier (the per-group barrier may be many phases ahead)
+    mbar_wait(&bars[4 + warp], 0);
+    t_end[warp] = clock64();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    long long b = t_begin[0], e = t_end[0];
+    for (int i = 1; i < nissuers; ++i) {
+      b = t_begin[i] < b ? t_begin[i] : b;
+      e = t_end[i] > e ? t_end[i] : e;
+    }
+    out[0] = e - b;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static void multi_case(int nissuers, int wait_each, char* report, size_t cap) {
+  long long* d = nullptr;
+  long long h[1] = {0};
+  const int groups = 256;
+  cudaMalloc(&d, sizeof(h));
+  cudaFuncSetAttribute(umma_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
+  umma_multi_kernel<<<1, 128, 66560>>>(nissuers, groups, wait_each, d);
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    rep(report, cap, "mma-multi/ CUDA-ERROR\n");
+    return;
+  }
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  rep(report, cap, "mma-multi/%d issuing threads x (8 MMAs N=32 + commit%s): %6.1f clk per MMA aggregate, %7.1f clk per group per thread\n",
+      nissuers, wait_each ? " + wait own commit" : "", (double)h[0] / (groups * 8.0 * nissuers), (double)h[0] / groups);
+}
+
 static void rep(char* buf, size_t cap, const char* fmt, ...) {
   size_t n = strlen(buf);
   if (n + 1 >= cap) return;
@@ -488,6 +556,8 @@ int umma_selftest(char* report, size_t cap) {
   commit_case(8, 3, report, cap);
   commit_case(4, 1, report, cap);
   commit_case(2, 2, report, cap);
+  for (int w = 0; w < 2; ++w)
+    for (int n = 1; n <= 3; ++n) multi_case(n, w, report, cap);
   mufu_case<0>("tanh.approx.f32", 4, report, cap);
   mufu_case<1>("ex2+rcp f32 (sigmoid)", 2, report, cap);
   mufu_case<2>("tanh.approx.bf16x2", 4, report, cap);
