@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
     const int row = quad * 32 + lane;              // query row inside the tile == TMEM lane
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
     const int i_pos = m0 + row;
-    const float ah = p.alpha_half;
+    const float2 ah2 = make_float2(p.alpha_half, p.alpha_half);
     const bool fast = msk.fast != 0;
     // plain causal (+targets): valid(i, j) = (j < lim_i) | (j == i)   (common.cuh: mask_valid, fast path)
     const int lim_i = msk.has_tgt ? min(i_pos, msk.max_id) : i_pos;
@@ -247,16 +247,18 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
         if (mode == 0) {
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const float h0 = __uint_as_float(s[e]) * ah, h1 = __uint_as_float(s[e + 1]) * ah;
-            const float p0 = fmaf(h0, tanh_approx(h0), h0), p1 = fmaf(h1, tanh_approx(h1), h1);
+            const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), ah2);
+            const float2 pv = __ffma2_rn(hh, make_float2(tanh_approx(hh.x), tanh_approx(hh.y)), hh);
+            const float p0 = pv.x, p1 = pv.y;
             pk[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
           }
         } else if (mode == 1) {
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             const int j0 = c * 32 + e;
-            const float h0 = __uint_as_float(s[e]) * ah, h1 = __uint_as_float(s[e + 1]) * ah;
-            float p0 = fmaf(h0, tanh_approx(h0), h0), p1 = fmaf(h1, tanh_approx(h1), h1);
+            const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), ah2);
+            const float2 pv = __ffma2_rn(hh, make_float2(tanh_approx(hh.x), tanh_approx(hh.y)), hh);
+            float p0 = pv.x, p1 = pv.y;
             p0 = ((j0 < lim_rel) | (j0 == diag_rel)) ? p0 : 0.f;
             p1 = ((j0 + 1 < lim_rel) | (j0 + 1 == diag_rel)) ? p1 : 0.f;
             pk[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
@@ -265,8 +267,9 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             const int j = n0 + c * 32 + e;
-            const float h0 = __uint_as_float(s[e]) * ah, h1 = __uint_as_float(s[e + 1]) * ah;
-            float p0 = fmaf(h0, tanh_approx(h0), h0), p1 = fmaf(h1, tanh_approx(h1), h1);
+            const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), ah2);
+            const float2 pv = __ffma2_rn(hh, make_float2(tanh_approx(hh.x), tanh_approx(hh.y)), hh);
+            float p0 = pv.x, p1 = pv.y;
             p0 = (j < len && mask_valid(msk, i_pos, j)) ? p0 : 0.f;
             p1 = (j + 1 < len && mask_valid(msk, i_pos, j + 1)) ? p1 : 0.f;
             pk[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);

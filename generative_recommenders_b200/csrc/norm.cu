@@ -69,13 +69,54 @@ struct RowIO {
   _Pragma("unroll") for (int i = 0; i < VEC; ++i)         \
     if (int c = (k * 32 + lane) * VEC + i; c < D)
 
-// counter-based uniform in [0,1): splitmix64 finaliser of (seed, index)
-__device__ __forceinline__ float uniform01(unsigned long long seed, unsigned long long idx) {
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+// Dropout decisions: counter-based, one splitmix64 finaliser of (seed, index / 4) yields the four 16-bit uniforms of four
+// consecutive elements (keep iff r16 >= round(p * 65536)).  Forward and backward -- and the vectorised and scalar paths --
+// evaluate the same function of the element index, so the masks always agree.  (One hash per element made the output
+// stage ALU-bound: ~90 integer instructions per element against ~10 for the rest of the kernel.)
+__device__ __forceinline__ unsigned long long dropout_hash4(unsigned long long seed, unsigned long long idx4) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx4 + 1);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint32_t dropout_threshold(float p) {
+  const float t = p * 65536.0f + 0.5f;
+  return t >= 65536.f ? 65536u : (uint32_t)t;  // p = 1 drops everything
+}
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, uint32_t thr) {
+  const unsigned long long z = dropout_hash4(seed, idx >> 2);
+  return (uint32_t)((z >> (16 * (idx & 3))) & 0xffffu) >= thr;
+}
+// v[] holds the lane's elements of one vector (RowIO layout) whose first element has flat index `base`
+template <int VEC, int PL>
+__device__ __forceinline__ void apply_dropout(float (&v)[PL], int len, int lane, unsigned long long base,
+                                              unsigned long long seed, uint32_t thr, float keep_scale) {
+  if constexpr (VEC % 4 == 0) {
+    // vector path: base and every chunk start are multiples of 4 (len % VEC == 0 is a precondition of this path)
+#pragma unroll
+    for (int k = 0; k < PL / VEC; ++k) {
+      const int c0 = (k * 32 + lane) * VEC;
+      if (c0 < len) {
+#pragma unroll
+        for (int g = 0; g < VEC / 4; ++g) {
+          const unsigned long long z = dropout_hash4(seed, (base + c0 + g * 4) >> 2);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool keep = (uint32_t)((z >> (16 * e)) & 0xffffu) >= thr;
+            v[k * VEC + g * 4 + e] = keep ? v[k * VEC + g * 4 + e] * keep_scale : 0.f;
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < PL / VEC; ++k)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int c = (k * 32 + lane) * VEC + i;
+        if (c < len) v[k * VEC + i] = dropout_keep(seed, base + c, thr) ? v[k * VEC + i] * keep_scale : 0.f;
+      }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -228,6 +269,7 @@ __global__ void __launch_bounds__(kNormThreads) nmd_fwd_kernel(const T* __restri
   }
   const float inv_d = 1.0f / (float)len;
   const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  const uint32_t thr = dropout_threshold(p);
   const long long n_vec = n_rows * G;
   for (long long vi = (long long)blockIdx.x * kNormWarps + warp; vi < n_vec; vi += (long long)gridDim.x * kNormWarps) {
     const long long r = vi / G;
@@ -260,15 +302,13 @@ __global__ void __launch_bounds__(kNormThreads) nmd_fwd_kernel(const T* __restri
     }
     T* orow = out + r * os + gidx * len;
     if (p > 0.f) {
-      FOR_OWNED(VEC, len, lane, k, i, c) {
-        const unsigned long long base = (unsigned long long)r * os + gidx * len + c;
-        if (concat) {
-          uu[k * VEC + i] = uniform01(seed, base) >= p ? uu[k * VEC + i] * keep_scale : 0.f;
-          a[k * VEC + i] = uniform01(seed, base + width) >= p ? a[k * VEC + i] * keep_scale : 0.f;
-          y[k * VEC + i] = uniform01(seed, base + 2 * width) >= p ? y[k * VEC + i] * keep_scale : 0.f;
-        } else {
-          y[k * VEC + i] = uniform01(seed, base) >= p ? y[k * VEC + i] * keep_scale : 0.f;
-        }
+      const unsigned long long base = (unsigned long long)r * os + gidx * len;
+      if (concat) {
+        apply_dropout<VEC, PL>(uu, len, lane, base, seed, thr, keep_scale);
+        apply_dropout<VEC, PL>(a, len, lane, base + width, seed, thr, keep_scale);
+        apply_dropout<VEC, PL>(y, len, lane, base + 2 * width, seed, thr, keep_scale);
+      } else {
+        apply_dropout<VEC, PL>(y, len, lane, base, seed, thr, keep_scale);
       }
     }
     if (concat) {
@@ -308,6 +348,7 @@ __global__ void __launch_bounds__(kNormThreads) nmd_bwd_kernel(
   }
   const float inv_d = 1.0f / (float)len;
   const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  const uint32_t thr = dropout_threshold(p);
   const long long n_vec = n_rows * G;
   for (long long vi = (long long)blockIdx.x * kNormWarps + warp; vi < n_vec; vi += (long long)gridDim.x * kNormWarps) {
     const long long r = vi / G;
@@ -326,15 +367,13 @@ __global__ void __launch_bounds__(kNormThreads) nmd_bwd_kernel(
       for (int i = 0; i < PL; ++i) gu[i] = ga[i] = 0.f;
     }
     if (p > 0.f) {
-      FOR_OWNED(VEC, len, lane, k, i, c) {
-        const unsigned long long base = (unsigned long long)r * os + gidx * len + c;
-        if (concat) {
-          gu[k * VEC + i] = uniform01(seed, base) >= p ? gu[k * VEC + i] * keep_scale : 0.f;
-          ga[k * VEC + i] = uniform01(seed, base + width) >= p ? ga[k * VEC + i] * keep_scale : 0.f;
-          gy[k * VEC + i] = uniform01(seed, base + 2 * width) >= p ? gy[k * VEC + i] * keep_scale : 0.f;
-        } else {
-          gy[k * VEC + i] = uniform01(seed, base) >= p ? gy[k * VEC + i] * keep_scale : 0.f;
-        }
+      const unsigned long long base = (unsigned long long)r * os + gidx * len;
+      if (concat) {
+        apply_dropout<VEC, PL>(gu, len, lane, base, seed, thr, keep_scale);
+        apply_dropout<VEC, PL>(ga, len, lane, base + width, seed, thr, keep_scale);
+        apply_dropout<VEC, PL>(gy, len, lane, base + 2 * width, seed, thr, keep_scale);
+      } else {
+        apply_dropout<VEC, PL>(gy, len, lane, base, seed, thr, keep_scale);
       }
     }
     const float mean = mean_in[vi], rstd = rstd_in[vi];
