@@ -52,31 +52,41 @@ struct BwdCfg {
   static constexpr int BOX_BYTES = 128 * SW;
   static constexpr int TILE_BYTES = 128 * D * 2;
   static constexpr int PT_BYTES = 128 * 128 * 2;          // one pair buffer: two [128 kv][64 q] boxes
-  static constexpr int STAGES = (D <= 32) ? 4 : 3;        // Q_i / dO_i TMA ring depth (d = 64: shared memory is full)
+  static constexpr int STAGES = (D <= 32) ? 4 : (D == 64 ? 3 : 1);  // Q_i / dO_i TMA ring depth (what shared memory allows)
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + TILE_BYTES;
   static constexpr int OFF_Q = OFF_V + TILE_BYTES;
   static constexpr int OFF_DO = OFF_Q + STAGES * TILE_BYTES;
   // dS^T boxes [kv][q] (tile i -> pair buffer i & 1): read K-major as A of dK (M = kv) and MN-major as A of dQ (M = q)
   static constexpr int OFF_DST = OFF_DO + STAGES * TILE_BYTES;
-  static constexpr int DQS_BYTES = 128 * D * 2;                  // per warpgroup: 128 query rows x D/2 fp32 columns
-  static constexpr int OFF_DQS = OFF_DST + 2 * PT_BYTES;         // dQ staging boxes (source of the TMA reduce-add)
+  // dQ staging (source of the TMA reduce-add): per warpgroup one box of 128 query rows x DQ_BOX_COLS fp32 columns; a
+  // warpgroup owns D/2 columns of dQ and sends them in DQ_NPASS boxes
+  static constexpr int DQ_BOX_COLS = (D / 2 < 32) ? D / 2 : 32;
+  static constexpr int DQ_NPASS = (D / 2) / DQ_BOX_COLS;
+  static constexpr int DQS_BYTES = 128 * DQ_BOX_COLS * 4;
+  static_assert(DQ_BOX_COLS * 4 == SW, "the staging box uses the operand swizzle width");
+  static constexpr int OFF_DQS = OFF_DST + 2 * PT_BYTES;
   static constexpr int OFF_BAR = OFF_DQS + 2 * DQS_BYTES;
   static_assert(OFF_BAR + 256 + 1024 <= 232448, "shared memory budget");
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   // TMEM: a ring of NSLOT score slots, each {S^T half-tile: 64 columns, dP^T half-tile: 64 columns} (a half-tile is
   // 128 key rows x 64 query rows; after the elementwise stage the front of the S^T half holds P^T as bf16), the dV and
-  // dK accumulators and TWO dQ accumulators (tile i -> buffer i & 1, so the warpgroups can drain dQ two tiles late and
-  // never wait for it).
-  static constexpr int NSLOT = (384 + 4 * D <= 512) ? 3 : 2;
+  // dK accumulators and NDQ dQ accumulators (tile i -> buffer i % NDQ; with two, the warpgroups drain dQ two tiles late and
+  // never wait for it).  d = 128 fills TMEM with one slot and one dQ accumulator: 128 + 3 * 128 columns.
+  static constexpr int NSLOT = (D <= 32) ? 3 : (D == 64 ? 2 : 1);
+  static constexpr int NDQ = (D <= 64) ? 2 : 1;
+  // s_full barrier instances: unit u -> [u % NSF].  At least two even with one slot: the warpgroups alternate units, and a
+  // warpgroup must never wait for phase k+1 of a barrier before phase k has completed (the parity test would pass at once).
+  static constexpr int NSF = NSLOT < 2 ? 2 : NSLOT;
+  static constexpr int LAG = NDQ;                // the warpgroups drain dQ of tile i - LAG after their unit of tile i
   static constexpr int TMEM_SLOT = 0;
   static constexpr int TMEM_DV = NSLOT * 128;
   static constexpr int TMEM_DK = TMEM_DV + D;
-  static constexpr int TMEM_DQ = TMEM_DK + D;   // two buffers of D columns
-  static_assert(TMEM_DQ + 2 * D <= 512, "TMEM budget");
+  static constexpr int TMEM_DQ = TMEM_DK + D;   // NDQ buffers of D columns
+  static_assert(TMEM_DQ + NDQ * D <= 512, "TMEM budget");
   // scripts/sim_bwd_protocol.py: a 3-slot score ring needs the Q/dO ring to be at least 4 deep (the scores of tile i+2 are
   // requested before tile i releases its stage), otherwise the producer and the MMA issuer wait on each other.
-  static_assert(NSLOT == 2 || STAGES >= 4, "3-slot score ring needs >= 4 Q/dO stages");
+  static_assert(NSLOT != 3 || STAGES >= 4, "3-slot score ring needs >= 4 Q/dO stages");
 };
 
 struct BwdBars {
@@ -230,7 +240,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
           const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
           mma_ss(ts + 64, dv_k + o, ddo_k + row_off + o, idesc_s, ks > 0);
         }
-        mma_commit(&bars->s_full[slot]);
+        mma_commit(&bars->s_full[u % Cfg::NSF]);
         HSTU_TSTAMP(0, u, 2);
       }
       __syncwarp();
@@ -283,14 +293,14 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       if (leader) HSTU_TSTAMP(4, i, 0);
       mbar_wait(&bars->unit_done[0 * 2 + pb], (i >> 1) & 1);
       mbar_wait(&bars->unit_done[1 * 2 + pb], (i >> 1) & 1);
-      if (i >= 2) mbar_wait(&bars->dq_empty[i & 1], ((i >> 1) - 1) & 1);  // dQ_{i-2} has been drained from this accumulator
+      if (i >= Cfg::NDQ) mbar_wait(&bars->dq_empty[i % Cfg::NDQ], ((i / Cfg::NDQ) - 1) & 1);  // dQ_{i-NDQ} has been drained from this accumulator
       tc_fence_after_sync();
       if (leader) {
         HSTU_TSTAMP(4, i, 1);
         const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);  // the dS^T boxes of this query tile
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows, 16 per step
-          mma_ss(tmem + Cfg::TMEM_DQ + (i & 1) * D, dds_mn + pair + (uint64_t)((ks * 16 * 128) >> 4),
+          mma_ss(tmem + Cfg::TMEM_DQ + (i % Cfg::NDQ) * D, dds_mn + pair + (uint64_t)((ks * 16 * 128) >> 4),
                  dk_mn + (uint64_t)((ks * 16 * SW) >> 4), idesc_dq, ks > 0);
         mma_commit(&bars->tile_done[i & 3]);
         HSTU_TSTAMP(4, i, 2);
@@ -320,27 +330,32 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     auto drain_dq = [&](int i) {
       mbar_wait(&bars->tile_done[i & 3], (i >> 2) & 1);
       tc_fence_after_sync();
-      if (dq_issuer) bulk_wait_group_read0();      // the previous reduce has finished reading the staging box
-      named_bar_sync(1 + wg, 128);
       const int qpos = q_tile(i) * 128 + row;
       const bool q_ok = qpos < len;                // rows past the end of this sequence belong to the next one: add zeros
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t r[16];
-        tmem_ld16(tmem + Cfg::TMEM_DQ + (i & 1) * D + qcol0 + c * 16 + lane_bits, r);
-        tmem_ld_wait();
+      for (int ps = 0; ps < Cfg::DQ_NPASS; ++ps) {
+        if (dq_issuer) bulk_wait_group_read0();    // the previous reduce has finished reading the staging box
+        named_bar_sync(1 + wg, 128);
 #pragma unroll
-        for (int e = 0; e < 16; e += 4)
-          st_shared_v4(sDQSw + swizzled_chunk_offset<SW>(row, c * 4 + (e >> 2)), q_ok ? r[e] : 0u, q_ok ? r[e + 1] : 0u,
-                       q_ok ? r[e + 2] : 0u, q_ok ? r[e + 3] : 0u);
-      }
-      tc_fence_before_sync();
-      mbar_arrive(&bars->dq_empty[i & 1]);
-      fence_proxy_async_smem();
-      named_bar_sync(1 + wg, 128);
-      if (dq_issuer) {
-        tma_reduce_add_3d(&p.tmDQ, sDQSw, qcol0, h, (int)(row0 + q_tile(i) * 128));
-        bulk_commit_group();
+        for (int c = 0; c < Cfg::DQ_BOX_COLS / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(tmem + Cfg::TMEM_DQ + (i % Cfg::NDQ) * D + qcol0 + ps * Cfg::DQ_BOX_COLS + c * 16 + lane_bits, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            st_shared_v4(sDQSw + swizzled_chunk_offset<SW>(row, c * 4 + (e >> 2)), q_ok ? r[e] : 0u, q_ok ? r[e + 1] : 0u,
+                         q_ok ? r[e + 2] : 0u, q_ok ? r[e + 3] : 0u);
+        }
+        if (ps == Cfg::DQ_NPASS - 1) {
+          tc_fence_before_sync();
+          mbar_arrive(&bars->dq_empty[i % Cfg::NDQ]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + wg, 128);
+        if (dq_issuer) {
+          tma_reduce_add_3d(&p.tmDQ, sDQSw, qcol0 + ps * Cfg::DQ_BOX_COLS, h, (int)(row0 + q_tile(i) * 128));
+          bulk_commit_group();
+        }
       }
     };
 
@@ -348,7 +363,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       const int u = 2 * i + wg, slot = u % Cfg::NSLOT;
       const int m0 = q_tile(i) * 128;
       if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 0);
-      mbar_wait(&bars->s_full[slot], (u / Cfg::NSLOT) & 1);
+      mbar_wait(&bars->s_full[u % Cfg::NSF], (u / Cfg::NSF) & 1);
       tc_fence_after_sync();
       if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 1);
       // classification of this half-tile (uniform over the warpgroup)
@@ -439,11 +454,10 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       fence_proxy_async_smem();
       if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 2);
       mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);
-      if (i >= 2) drain_dq(i - 2);  // two tiles late: dQ_{i-2} finished long ago, no stall
+      if (i >= Cfg::LAG) drain_dq(i - Cfg::LAG);  // LAG = 2: dQ_{i-2} finished long ago, no stall
       if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 3);
     }
-    if (T >= 2) drain_dq(T - 2);
-    drain_dq(T - 1);
+    for (int t = (T > Cfg::LAG ? T - Cfg::LAG : 0); t < T; ++t) drain_dq(t);
     if (dq_issuer) bulk_wait_group_read0();      // shared memory must stay valid until the last reduce has read it
     // ---------------- epilogue: dV (warpgroup 0) / dK (warpgroup 1): TMEM -> scale -> global ----------------
     mbar_wait(&bars->fin_full, 0);
@@ -509,7 +523,7 @@ static bool aligned_view(const void* ptr, long long row_stride, long long head_s
 
 static bool umma_bwd_supported(const hstu_attn_params& p) {
   if (!umma_fwd_supported(p)) return false;  // dtype / dims / alignment of q, k, v (out is not used by the backward)
-  if (p.dqk != 32 && p.dqk != 64) return false;
+  if (p.dqk != 32 && p.dqk != 64 && p.dqk != 128) return false;
   return aligned_view(p.dout, p.do_row_stride, p.do_head_stride) && aligned_view(p.dq, p.dq_row_stride, p.dq_head_stride) &&
          aligned_view(p.dk, p.dk_row_stride, p.dk_head_stride) && aligned_view(p.dv_out, p.dv_row_stride, p.dv_head_stride);
 }
@@ -542,7 +556,7 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   if (int e = make_tmap_rows_heads(&bp.tmK, p.k, p.total_rows, p.heads, D, p.k_row_stride, p.k_head_stride, Cfg::BOX_COLS, 128)) return e;
   if (int e = make_tmap_rows_heads(&bp.tmV, p.v, p.total_rows, p.heads, D, p.v_row_stride, p.v_head_stride, Cfg::BOX_COLS, 128)) return e;
   if (int e = make_tmap_rows_heads(&bp.tmDO, p.dout, p.total_rows, p.heads, D, p.do_row_stride, p.do_head_stride, Cfg::BOX_COLS, 128)) return e;
-  if (int e = make_tmap_rows_heads_f32(&bp.tmDQ, p.workspace, p.total_rows, p.heads, D, D / 2, 128)) return e;
+  if (int e = make_tmap_rows_heads_f32(&bp.tmDQ, p.workspace, p.total_rows, p.heads, D, Cfg::DQ_BOX_COLS, 128)) return e;
   bp.seq_offsets = p.seq_offsets;
   bp.num_targets = p.num_targets;
   bp.dk = p.dk;
@@ -608,6 +622,7 @@ int attn_umma_bwd(const hstu_attn_params& p, cudaStream_t st) {
   switch (p.dqk) {
     case 32: return bf ? launch_bwd_umma<32, true>(p, st) : launch_bwd_umma<32, false>(p, st);
     case 64: return bf ? launch_bwd_umma<64, true>(p, st) : launch_bwd_umma<64, false>(p, st);
+    case 128: return bf ? launch_bwd_umma<128, true>(p, st) : launch_bwd_umma<128, false>(p, st);
   }
   set_error("tcgen05 backward: unsupported head dim %d", p.dqk);
   return HSTU_ERR_UNSUPPORTED;

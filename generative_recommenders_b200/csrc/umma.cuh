@@ -28,8 +28,8 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-#ifndef HSTU_SPIN_LIMIT
-#define HSTU_SPIN_LIMIT (1u << 28)  // bounded spin: a protocol bug traps instead of hanging the GPU
+#ifndef HSTU_WAIT_LIMIT_CLK
+#define HSTU_WAIT_LIMIT_CLK 4000000000ll  // bounded wait (~2 s): a protocol bug traps instead of hanging the GPU
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -73,9 +73,12 @@ __device__ __forceinline__ void mbar_wait_line(uint64_t* bar, uint32_t parity, i
 #define mbar_wait(bar, parity) mbar_wait_line(bar, parity, __LINE__)
 #else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  // bounded in TIME (try_wait may suspend the thread for a while, so a spin COUNT bounds nothing): a protocol bug traps
+  // after ~2 s instead of hanging the GPU
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > HSTU_SPIN_LIMIT) __trap();
+    if (clock64() - t0 > HSTU_WAIT_LIMIT_CLK) __trap();
   }
 }
 #endif
