@@ -57,6 +57,19 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic(cfg):
+    """DRAM bytes per launch of the attention backward kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py) -- only if it was taken on this attention shape."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(path))
+        if d.get("attn_shape") == cfg.get("attn_shape"):
+            return d["kernels"]["attn_bwd"]["dram_bytes"], f"profiles/ncu_traffic.json ({d['source']}; {d['workload']})"
+    except Exception:
+        pass
+    return None, None
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
 
@@ -200,6 +213,7 @@ def run_ours(args):
                "global_batch": args.batch * world, "seq_len": args.lmax, "rows_per_gpu": L,
                "parallelism": f"dp{world} (batch-sharded, per-layer NCCL all-reduce of grads overlapped with backward)",
                "l2": f"inputs + activations per step ({L * D * 2 * 6 / 1e6:.0f} MB+) exceed the 126 MB L2; no explicit flush"}
+        cfg["attn_shape"] = {"batch": args.batch, "lmax": args.lmax, "heads": H, "d": dh}
         aflops = attn_flops(lengths, H, dh, dh)
         abytes = attn_bytes(lengths, H, dh, dh)
         per_step_calls = layers
@@ -234,6 +248,7 @@ def run_ours(args):
                            f"Lmax={args.lmax}, bf16, alpha=1/d, targets<=20", "global_batch": args.batch * world,
                "seq_len": args.lmax, "rows_per_gpu": L, "parallelism": f"dp{world} (independent shards)",
                "l2": f"q,k,v,o,grads = {L * Ha * d * 2 * 11 / 1e6:.0f} MB per step > 126 MB L2" }
+        cfg["attn_shape"] = {"batch": args.batch, "lmax": args.lmax, "heads": Ha, "d": d}
         aflops = attn_flops(lengths, Ha, d, d)
         abytes = attn_bytes(lengths, Ha, d, d)
         per_step_calls = 1
@@ -293,9 +308,11 @@ def run_ours(args):
         tf_b = aflops["bwd"] / (kt["attn_bwd"] * 1e-3) / 1e12
         tf_f = aflops["fwd"] / (kt["attn_fwd"] * 1e-3) / 1e12
         peak = peaks["tflops_sustained"]
+        traffic, traffic_src = ncu_traffic(cfg)
         out["roofline"] = {
             "kernel": "hstu_attn_bwd (dK/dV + dQ kernels of one layer call)", "bound": "tensor", "achieved": tf_b, "peak": peak,
-            "unit": "TFLOP/s", "frac": tf_b / peak, "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+            "unit": "TFLOP/s", "frac": tf_b / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peaks["source"] + ", sustained bf16",
             "ms_per_launch": kt["attn_bwd"], "algorithmic_flops_per_launch": aflops["bwd"],
             "fwd": {"achieved": tf_f, "frac": tf_f / peak, "ms_per_launch": kt["attn_fwd"],
                     "algorithmic_flops_per_launch": aflops["fwd"],

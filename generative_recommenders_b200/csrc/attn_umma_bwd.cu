@@ -1,21 +1,23 @@
-// Jagged HSTU attention backward on tcgen05 + TMEM with TMA-staged tiles.  bf16 / fp16, dqk == dv in {32, 64}.
+// Jagged HSTU attention backward on tcgen05 + TMEM with TMA-staged tiles.  bf16 / fp16, dqk == dv in {32, 64, 128}.
 //
 // One CTA per (128-row KEY tile, head, sequence); early key tiles (the heavy ones under a causal mask) are scheduled
 // first.  K and V of the tile stay in shared memory; the CTA streams the query tiles that can attend to it
-// (Q_i and dO_i, TMA ring of 2-4 stages).  Work is pipelined in half-tiles ("units": 128 key rows x 64 query rows):
-//     S^T  = K Q^T            (A = K  K-major,  B = 64 rows of Q_i  K-major)   -> TMEM slot, columns [0, 64)
-//     dP^T = V dO^T           (A = V  K-major,  B = 64 rows of dO_i K-major)   -> TMEM slot, columns [64, 128)
-//   The slots form a ring of 3 (2 for d = 64): the scores of unit u+3 are issued as soon as unit u has been read, so
-//   the two elementwise warpgroups (warpgroup h owns half h of every query tile; one key row per thread) always find
-//   their next scores ready.  They turn S^T, dP^T into
+// (Q_i and dO_i, TMA ring of 4 / 3 / 1 stages for d = 32 / 64 / 128).  Work is pipelined in half-tiles ("units":
+// 128 key rows x 64 query rows); three warps issue MMAs, each with its own wait -> issue -> commit loop:
+//   X:  S^T  = K Q^T          (A = K  K-major,  B = 64 rows of Q_i  K-major)   -> TMEM slot, columns [0, 64)
+//       dP^T = V dO^T         (A = V  K-major,  B = 64 rows of dO_i K-major)   -> TMEM slot, columns [64, 128)
+//   The slots form a ring of 3 / 2 / 1.  The two elementwise warpgroups (warpgroup h owns half h of every query tile; one
+//   key row per thread) turn S^T, dP^T into
 //        P^T  = silu(alpha S)            * mask      (1/N folded into the dV epilogue)
 //        dS^T = dP sig (1 + x (1 - sig)) * mask      (alpha/N folded into the dK epilogue / dQ convert)
-//   from ONE tanh per score and write them as bf16 boxes ([kv][q], q contiguous, 128B swizzle; two box pairs) --
-//     dV  += P^T  dO          (A = P^T box  K-major,  B = 64 rows of dO_i MN-major)   [kv x d]  all query tiles
-//     dK  += dS^T Q           (A = dS^T box K-major,  B = 64 rows of Q_i  MN-major)   [kv x d]
-//     dQ_i = dS   K           (A = both dS^T boxes of the tile read MN-major, B = K MN-major)   [128 q x d]
-//   dQ_i is added to an fp32 accumulator in global memory with 128-bit vector reductions (each key-tile CTA
-//   contributes to every later query tile); a small convert kernel scales it by alpha/N and writes bf16 dq.
+//   from ONE tanh per score (packed fp32x2 arithmetic).  P^T (bf16) overwrites the front of the slot in TMEM, dS^T goes to a
+//   bf16 box in shared memory ([kv][q], q contiguous, 128B swizzle; two box pairs).
+//   Y:  dV  += P^T  dO        (A = P^T from the TMEM slot,  B = 64 rows of dO_i MN-major)   [kv x d]  all query tiles
+//   Z:  dK  += dS^T Q         (A = dS^T box K-major,  B = 64 rows of Q_i  MN-major)         [kv x d]
+//       dQ_i = dS   K         (A = both dS^T boxes of the tile read MN-major, B = K MN-major)   [128 q x d]
+//   dQ_i (two TMEM accumulators, drained two tiles late) is staged as fp32 in a swizzled shared-memory box and added to an
+//   fp32 accumulator in global memory with one TMA reduce-add per warpgroup (each key-tile CTA contributes to every later
+//   query tile); a small convert kernel scales it by alpha/N and writes bf16 dq.
 //
 // Reference math: ops/triton/triton_hstu_attention.py:995-1006,1222 and SURVEY.md appendix A; unlike the Triton
 // kernel dQ is accumulated in fp32, not in the input dtype (triton_attention_utils.py:47-60).

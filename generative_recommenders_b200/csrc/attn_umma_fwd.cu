@@ -2,14 +2,17 @@
 // dqk == dv in {32, 64, 128}.
 //
 // One CTA per (128-row query tile, head, sequence); heavy (late) query tiles are scheduled first.  Warp roles:
-//   warp 0  lane 0 : TMA producer for Q (once) and the K tiles          (2-stage ring, mbarrier full/empty)
-//   warp 3  lane 0 : TMA producer for the V tiles                      (2-stage ring)
-//   warp 1  lane 0 : tcgen05.mma issuer:  S_t = Q K_t^T  (SS, both K-major)  and  O += P_t V_t  (A = P in smem,
-//                    B = V MN-major), S in a 3-deep TMEM ring, O accumulated in TMEM across all key tiles
-//   warp 2         : TMEM allocation / release
+//   warp 0  lane 0 : TMA producer for Q (once) and the K tiles (3 stages; stage t % 3 is reused once s_full of tile t
+//                    has completed, i.e. the score GEMM has read it)
+//   warp 3  lane 0 : TMA producer for the V tiles (3 stages, reused once pv_done of tile t has completed)
+//   warp 1  lane 0 : tcgen05.mma issuer 1:  S_t = Q K_t^T  (SS, both K-major) into TMEM slot t % 3, one commit per tile
+//   warp 2         : TMEM allocation / release; lane 0 = issuer 2:  O += P_t V_t  (TS: A = P_t read from the front of
+//                    slot t % 3, B = V_t MN-major), rotating over NACC accumulators, one commit per tile.
+//                    Two issuing threads because tcgen05.commit and the barrier waits stall only their own issuer
+//                    (umma_selftest: one thread 71 clk / MMA, two threads 40).
 //   warps 4-7, 8-11: two "silu" warpgroups.  Warpgroup g owns key tiles t = g, g+2, ...: tcgen05.ld S (one query row per
-//                    thread), p = silu(alpha*s) * mask via one MUFU (tanh) + 2 FMA-pipe ops, packs bf16 pairs and writes
-//                    them 16 B at a time into the 128B-swizzled K-major P tile that feeds the second MMA.
+//                    thread, next 32 columns prefetched), p = silu(alpha*s) * mask via one MUFU (tanh) + packed fp32x2
+//                    FMUL2 / FFMA2, packs bf16 pairs and writes them with tcgen05.st over the S columns already read.
 // The 1/N factor of the reference is applied once in the epilogue (O tile: TMEM -> registers -> 128-bit global stores,
 // rows past the sequence end are not written).  Rows of neighbouring sequences that a 128-row TMA box drags in are
 // neutralised by the mask (P = 0 for key positions >= len), never by re-reading memory.

@@ -1,101 +1,177 @@
 #!/usr/bin/env python3
-"""Discrete simulation of the mbarrier protocol of attn_bwd_umma_kernel (deadlock / phase-aliasing check on CPU).
-Each actor is a generator yielding ('wait', bar, parity) | ('arrive', bar) | ('commit', bar) | ('tma', bar)."""
-import itertools, random, sys
+"""Discrete simulation of the mbarrier protocol of attn_bwd_umma_kernel (csrc/attn_umma_bwd.cu) on the CPU.
+
+Checks, under random schedules, that (1) nobody deadlocks, (2) no parity wait "passes falsely" -- a waiter asking for
+phase k of a barrier while phase k-1 has not completed sees the parity test succeed at once -- and (3) no waiter falls two
+phases behind (its parity test would then block until the barrier wraps).  Both bugs happened on the GPU during
+development (unit_done with a 3-slot ring; s_full with a single slot); this model reproduces them when the fix is removed
+(--break-ud / --break-sf).
+
+Actors: P producer, X (scores), Y (dV), Z (dK, dQ), W0 / W1 elementwise warpgroups.  tcgen05.commit and TMA completions are
+asynchronous: they are queued per issuing actor and fire later, in order.
+usage: sim_bwd_protocol.py [--d 32|64|128] [--tiles T] [--seeds N] [--break-ud] [--break-sf]"""
+import argparse, random
+
 
 class Bar:
-    def __init__(self, count): self.count=count; self.pending=count; self.phase=0
+    def __init__(self, count):
+        self.count, self.pending, self.phase = count, count, 0
+
     def arrive(self):
-        self.pending-=1
-        if self.pending==0: self.pending=self.count; self.phase+=1
-    def done(self, parity):  # try_wait.parity semantics: true iff the phase with this parity has completed most recently
-        return (self.phase & 1) != parity if False else ((self.phase-1) & 1)==parity and self.phase>0 or False
+        self.pending -= 1
+        if self.pending == 0:
+            self.pending, self.phase = self.count, self.phase + 1
 
-def try_wait(bar, parity):
-    # mbarrier phase bit starts at 0; wait(parity) succeeds when current phase parity != parity  (i.e. phase `parity` completed)
-    return (bar.phase & 1) != parity
 
-def run(T, NST, NSLOT, seed):
-    rnd=random.Random(seed)
-    slow=rnd.choice(['prod','mma','wgA','wgB',None])
-    B={'kv':Bar(1),'fin':Bar(1),'dq_full':Bar(1),'dq_empty':Bar(2)}
-    for i in range(NST): B[f'qf{i}']=Bar(1); B[f'qe{i}']=Bar(1)
-    for i in range(3): B[f'sf{i}']=Bar(1)
-    for i in range(4): B[f'ud{i}']=Bar(1)
-    for i in range(2): B[f'pe{i}']=Bar(1)
-    U=2*T
-    log=[]
+class Violation(Exception):
+    pass
+
+
+def cfg_for(d):
+    return dict(NST={32: 4, 64: 3, 128: 1}[d], NSLOT={32: 3, 64: 2, 128: 1}[d], NDQ={32: 2, 64: 2, 128: 1}[d])
+
+
+def run(T, d, seed, break_ud=False, break_sf=False):
+    c = cfg_for(d)
+    NST, NSLOT, NDQ = c["NST"], c["NSLOT"], c["NDQ"]
+    NSF = NSLOT if break_sf else max(NSLOT, 2)
+    LAG = NDQ
+    rnd = random.Random(seed)
+    B = {"kv": Bar(1), "fin": Bar(2)}
+    for i in range(4):
+        B[f"qf{i}"] = Bar(1)
+        B[f"td{i}"] = Bar(2)
+        B[f"ud{i}"] = Bar(1)       # count 128 threads modelled as one arrival per warpgroup
+    for i in range(3):
+        B[f"sf{i}"] = Bar(1)
+        B[f"free{i}"] = Bar(1)
+    for i in range(2):
+        B[f"dqe{i}"] = Bar(2)      # both warpgroups
+    U = 2 * T
+
+    def ud(u):  # barrier instance and phase index of unit_done for unit u
+        i, hf = u >> 1, u & 1
+        if break_ud:
+            return f"ud{hf}", i                     # one barrier per half: aliases with a 3-slot ring
+        return f"ud{hf * 2 + (i & 1)}", i >> 1
+
     def producer():
-        yield ('tma','kv')
+        yield ("async", "kv")
         for i in range(T):
-            st=i%NST
-            if i>=NST: yield ('wait',f'qe{st}',((i//NST)-1)&1)
-            yield ('tma',f'qf{st}')
-    def mma():
-        def issue_s(u):
-            i,hf=u>>1,u&1; st=i%NST; slot=u%NSLOT
-            if hf==0: yield ('wait',f'qf{st}',(i//NST)&1)
-            yield ('commit',f'sf{slot}')
-        yield ('wait','kv',0)
-        for u in range(min(NSLOT,U)):
-            yield from issue_s(u)
-        for u in range(U):
-            i,hf=u>>1,u&1; st=i%NST; pb=i&1
-            yield ('wait',f'ud{hf*2+pb}',(i>>1)&1)
-            if u+NSLOT<U: yield from issue_s(u+NSLOT)
-            if hf==1:
-                if i>=1: yield ('wait','dq_empty',(i-1)&1)
-                yield ('commit',f'qe{st}'); yield ('commit',f'pe{pb}'); yield ('commit','dq_full')
-        yield ('commit','fin')
-    def wg(w):
-        def drain(i):
-            yield ('wait','dq_full',i&1)
-            yield ('arrive','dq_empty')
-        for i in range(T):
-            u=2*i+w; slot=u%NSLOT
-            yield ('wait',f'sf{slot}',(u//NSLOT)&1)
-            if i>=2: yield ('wait',f'pe{i&1}',((i>>1)-1)&1)
-            yield ('arrive',f'ud{w*2+(i&1)}')
-            if i>=1: yield from drain(i-1)
-        yield from drain(T-1)
-        yield ('wait','fin',0)
-    actors={'prod':producer(),'mma':mma(),'wgA':wg(0),'wgB':wg(1)}
-    cur={k:None for k in actors}
-    alive=set(actors)
-    async_q=[]  # pending async completions (commits / tma), delivered in order with random delay
-    steps=0
-    while alive:
-        steps+=1
-        progressed=False
-        order=list(alive); rnd.shuffle(order)
-        # deliver async completions randomly (in order)
-        if async_q and rnd.random()<0.5:
-            B[async_q.pop(0)].arrive(); progressed=True
-        for a in order:
-            if a==slow and rnd.random()<0.9: continue   # adversarial: one actor is much slower than the others
-            if cur[a] is None:
-                try: cur[a]=next(actors[a])
-                except StopIteration: alive.discard(a); progressed=True; continue
-            op=cur[a]
-            if op[0]=='wait':
-                if try_wait(B[op[1]],op[2]): cur[a]=None; progressed=True
-            elif op[0]=='arrive':
-                B[op[1]].arrive(); cur[a]=None; progressed=True
-            else:  # commit / tma: asynchronous completion
-                async_q.append(op[1]); cur[a]=None; progressed=True
-        if not progressed:
-            if async_q: B[async_q.pop(0)].arrive(); continue
-            if slow is not None: slow=None; continue
-            return False,{a:cur[a] for a in alive},{k:(b.phase,b.pending) for k,b in B.items()}
-    return True,None,None
+            if i >= NST:
+                yield ("wait", f"td{(i - NST) & 3}", (i - NST) >> 2)
+            yield ("async", f"qf{i % NST}")
 
-bad=0
-for T in range(1,12):
-    for NST in (2,4):
-        for NSLOT in (2,3):
-            for seed in range(60):
-                ok,blocked,state=run(T,NST,NSLOT,seed)
-                if not ok:
-                    bad+=1
-                    if bad<4: print('DEADLOCK T',T,'NST',NST,'NSLOT',NSLOT,'seed',seed,blocked,state)
-print('bad',bad)
+    def X():
+        yield ("wait", "kv", 0)
+        for u in range(U):
+            i, hf = u >> 1, u & 1
+            if u >= NSLOT:
+                yield ("wait", f"free{u % NSLOT}", u // NSLOT - 1)
+            if hf == 0:
+                yield ("wait", f"qf{i % NST}", i // NST)
+            yield ("async", f"sf{u % NSF}")
+
+    def Y():
+        for u in range(U):
+            i, hf = u >> 1, u & 1
+            yield ("wait",) + ud(u)
+            yield ("async", f"free{u % NSLOT}")
+            if hf == 1:
+                yield ("async", f"td{i & 3}")
+        yield ("async", "fin")
+
+    def Z():
+        for u in range(U):
+            i, hf = u >> 1, u & 1
+            yield ("wait",) + ud(u)
+            if hf == 1:
+                if i >= NDQ:
+                    yield ("wait", f"dqe{i % NDQ}", i // NDQ - 1)
+                yield ("async", f"td{i & 3}")
+        yield ("async", "fin")
+
+    def W(h):
+        def drain(i):
+            yield ("wait", f"td{i & 3}", i >> 2)
+            yield ("arrive", f"dqe{i % NDQ}")
+        for i in range(T):
+            u = 2 * i + h
+            yield ("wait", f"sf{u % NSF}", u // NSF)
+            if i >= 2:
+                yield ("wait", f"td{(i - 2) & 3}", (i - 2) >> 2)
+            yield ("arrive", ud(u)[0])
+            if i >= LAG:
+                yield from drain(i - LAG)
+        for t in range(max(0, T - LAG), T):
+            yield from drain(t)
+        yield ("wait", "fin", 0)
+
+    actors = {"P": producer(), "X": X(), "Y": Y(), "Z": Z(), "W0": W(0), "W1": W(1)}
+    pending = {k: None for k in actors}     # the blocking wait of each actor
+    queues = {k: [] for k in actors}        # asynchronous completions (commit / TMA), in order per actor
+    done = set()
+    steps = 0
+    while len(done) < len(actors) or any(queues.values()):
+        steps += 1
+        if steps > 200000:
+            raise Violation("no progress (livelock?)")
+        choices = [("run", k) for k in actors if k not in done] + [("fire", k) for k, q in queues.items() if q]
+        rnd.shuffle(choices)
+        progressed = False
+        for kind, k in choices:
+            if kind == "fire":
+                B[queues[k].pop(0)].arrive()
+                progressed = True
+                break
+            if pending[k] is None:
+                try:
+                    pending[k] = next(actors[k])
+                except StopIteration:
+                    done.add(k)
+                    progressed = True
+                    break
+            op = pending[k]
+            if op[0] == "wait":
+                _, name, want = op
+                bar = B[name]
+                passes = (bar.phase & 1) != (want & 1)          # try_wait.parity semantics
+                if passes and bar.phase <= want:
+                    raise Violation(f"{k}: wait on {name} for phase {want} passed while the barrier is in phase {bar.phase} (false pass)")
+                if not passes and bar.phase > want:
+                    raise Violation(f"{k}: wait on {name} for phase {want} but the barrier is already in phase {bar.phase} (two ahead)")
+                if not passes:
+                    continue
+            elif op[0] == "arrive":
+                B[op[1]].arrive()
+            elif op[0] == "async":
+                queues[k].append(op[1])
+            pending[k] = None
+            progressed = True
+            break
+        if not progressed:
+            state = {k: pending[k] for k in actors if k not in done}
+            raise Violation(f"deadlock: {state}")
+    return steps
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--d", type=int, default=0)
+    ap.add_argument("--tiles", type=int, default=0)
+    ap.add_argument("--seeds", type=int, default=200)
+    ap.add_argument("--break-ud", action="store_true")
+    ap.add_argument("--break-sf", action="store_true")
+    a = ap.parse_args()
+    bad = 0
+    for d in ([a.d] if a.d else [32, 64, 128]):
+        for T in ([a.tiles] if a.tiles else [1, 2, 3, 4, 5, 8, 13, 64]):
+            for seed in range(a.seeds):
+                try:
+                    run(T, d, seed, a.break_ud, a.break_sf)
+                except Violation as e:
+                    bad += 1
+                    if bad <= 5:
+                        print(f"d={d} T={T} seed={seed}: {e}")
+    print("violations:", bad)
+    raise SystemExit(1 if bad else 0)

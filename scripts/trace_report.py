@@ -1,19 +1,30 @@
-"""Summarise gpurun_out/bwd_trace.txt (HSTU_TRACE build of the backward kernel): per-actor phase durations in clocks."""
+"""Summarise gpurun_out/bwd_trace.txt (HSTU_TRACE build of the backward kernel, CTA (0,0,0)): merged event timeline in clocks.
+
+roles: 0 = issuer X (scores), 1 = issuer Y (dV), 4 = issuer Z (dK, dQ), 2/3 = elementwise warpgroups 0/1.
+usage: trace_report.py [trace] [first_unit] [n_units]"""
 import collections, sys
+path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/bwd_trace.txt"
+u0 = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+nu = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 rows = collections.defaultdict(dict)
-for l in open(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/bwd_trace.txt"):
+for l in open(path):
     p = l.split()
-    if len(p) < 6: continue
-    rows[int(p[0])][int(p[1])] = [int(x) for x in p[2:6]]
+    if len(p) >= 6: rows[int(p[0])][int(p[1])] = [int(x) for x in p[2:6]]
 t0 = min(v[0] for v in rows[0].values() if v[0])
-lo, hi = 20, 32
-for u in range(lo, hi):
-    a = rows[0][u]; n = rows[0].get(u + 1, [0])[0]
-    print('X', u, a[0] - t0, 'pre(dV wait+issue, q_full)', a[1] - a[0], 'scores+commit', a[2] - a[1], 'gap', n - a[2])
-for u in range(lo, hi):
-    a = rows[1][u]; n = rows[1].get(u + 1, [0])[0]
-    print('Y', u, a[0] - t0, 'wait_unit', a[1] - a[0], 'dK', a[2] - a[1], 'dq_empty wait', (a[3] - a[2]) if a[3] else '-', 'dQ+commit', n - (a[3] if a[3] else a[2]))
+ev = []
+for u in range(u0, u0 + nu):
+    a = rows[0].get(u)
+    if a: ev += [(a[0] - t0, f'X  u{u} waits slot_free / q_full'), (a[1] - t0, f'X  u{u} issues S^T, dP^T'), (a[2] - t0, f'X  u{u} commit issued')]
+    a = rows[1].get(u)
+    if a: ev += [(a[0] - t0, f'Y  u{u} waits unit_done'), (a[1] - t0, f'Y  u{u} issues dV'), (a[2] - t0, f'Y  u{u} commits issued')]
+    a = rows[4].get(u) or rows[4].get(u // 2)
+    if a: ev += [(a[0] - t0, f'Z  u{u} waits unit_done'), (a[1] - t0, f'Z  u{u} issues dK/dQ'), (a[2] - t0, f'Z  u{u} issued')]
 for wg in (0, 1):
-    for i in range(lo // 2, hi // 2):
-        a = rows[2 + wg][i]
-        print('WG', wg, i, a[0] - t0, 'wait_s', a[1] - a[0], 'elem', a[2] - a[1], 'drain', a[3] - a[2])
+    for i in range(u0 // 2, (u0 + nu) // 2 + 1):
+        a = rows[2 + wg].get(i)
+        if a:
+            u = 2 * i + wg
+            ev += [(a[0] - t0, f'W{wg} u{u} waits s_full'), (a[1] - t0, f'W{wg} u{u} elementwise starts'),
+                   (a[2] - t0, f'W{wg} u{u} arrives unit_done, drains dQ'), (a[3] - t0, f'W{wg} u{u} drain done')]
+for t, e in sorted(set(ev)):
+    print(f'{t:8d}  {e}')
