@@ -1,0 +1,129 @@
+"""Research-path HSTU block on the B200 ops.
+
+Mirrors generative_recommenders/research/modeling/sequential/hstu.py:
+  * `RelativeBucketedTimeAndPositionBasedBias` (:87-144) -- here only the parameter container (`_ts_w [num_buckets + 1]`,
+    `_pos_w [2 n - 1]`); the bias itself is evaluated inside the attention kernel, never materialised as [B, n, n].
+  * `SequentialTransductionUnitJagged` (:226-444), normalization "rel_bias" / "hstu_rel_bias", linear_config "uvqk",
+    training / full-sequence forward:  LN (no affine) -> mm -> SiLU on all of uvqk -> split u|v|q|k ->
+    silu(q k^T + rel_bias) / n under the causal mask -> u * LN(attn)  (or cat[u, a, u*a], a = LN(attn)) -> dropout ->
+    Linear(+bias) + x.
+Parameter names (`_uvqk`, `_o.weight`, `_o.bias`, `_rel_attn_bias._ts_w`, `_rel_attn_bias._pos_w`) are the reference's, so
+its state dicts load unchanged.  The incremental-decoding arguments (`delta_x_offsets`, `cache`) and the
+"softmax_rel_bias" ablation are not part of this round and raise.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from ..common import HammerKernel, HammerModule
+from ..ops.hstu_attention import hstu_rel_bias_attention
+from ..ops.hstu_compute import _SiluFunction, hstu_compute_output
+from ..ops.layer_norm import layer_norm
+
+
+class RelativeBucketedTimeAndPositionBasedBias(torch.nn.Module):
+    """Parameters of the bucketed time + position bias (research hstu.py:87-108).  `bucketization_fn` is fixed to the one the
+    reference configures (`floor(log(max(|dt|, 1)) / 0.301)`, hstu.py:610-612): it is compiled into the attention kernel."""
+
+    def __init__(self, max_seq_len: int, num_buckets: int = 128) -> None:
+        super().__init__()
+        self._max_seq_len = max_seq_len
+        self._num_buckets = num_buckets
+        self._ts_w = torch.nn.Parameter(torch.empty(num_buckets + 1).normal_(mean=0, std=0.02))
+        self._pos_w = torch.nn.Parameter(torch.empty(2 * max_seq_len - 1).normal_(mean=0, std=0.02))
+
+
+class SequentialTransductionUnitJagged(HammerModule):
+    def __init__(
+        self,
+        embedding_dim: int,
+        linear_hidden_dim: int,
+        attention_dim: int,
+        dropout_ratio: float,
+        attn_dropout_ratio: float,
+        num_heads: int,
+        linear_activation: str,
+        relative_attention_bias_module: Optional[RelativeBucketedTimeAndPositionBasedBias] = None,
+        normalization: str = "rel_bias",
+        linear_config: str = "uvqk",
+        concat_ua: bool = False,
+        epsilon: float = 1e-6,
+        max_length: Optional[int] = None,
+    ) -> None:
+        super().__init__()
+        if linear_config != "uvqk":
+            raise ValueError(f"Unknown linear_config {linear_config}")
+        if normalization not in ("rel_bias", "hstu_rel_bias"):
+            raise NotImplementedError(f"normalization {normalization!r}: only the HSTU (silu) attention is built for B200")
+        if linear_activation != "silu":
+            raise NotImplementedError("linear_activation must be 'silu' (the setting of every reference config)")
+        if relative_attention_bias_module is None:
+            raise ValueError("relative_attention_bias_module is required for rel_bias normalization (hstu.py:342)")
+        if attn_dropout_ratio != 0.0:
+            raise NotImplementedError("attention dropout is not supported (unused by the reference's own path, hstu.py:150-223)")
+        self._embedding_dim = embedding_dim
+        self._linear_dim = linear_hidden_dim
+        self._attention_dim = attention_dim
+        self._dropout_ratio = dropout_ratio
+        self._attn_dropout_ratio = attn_dropout_ratio
+        self._num_heads = num_heads
+        self._rel_attn_bias = relative_attention_bias_module
+        self._normalization = normalization
+        self._linear_config = linear_config
+        self._linear_activation = linear_activation
+        self._concat_ua = concat_ua
+        self._eps = epsilon
+        self._uvqk = torch.nn.Parameter(
+            torch.empty((embedding_dim, linear_hidden_dim * 2 * num_heads + attention_dim * num_heads * 2)).normal_(mean=0, std=0.02))
+        self._o = torch.nn.Linear(in_features=linear_hidden_dim * num_heads * (3 if concat_ua else 1), out_features=embedding_dim)
+        torch.nn.init.xavier_uniform_(self._o.weight)
+        # LayerNorm without affine parameters (hstu.py:276-282) = the affine kernel with constant ones / zeros
+        self.register_buffer("_ones_in", torch.ones(embedding_dim), persistent=False)
+        self.register_buffer("_zeros_in", torch.zeros(embedding_dim), persistent=False)
+        self.register_buffer("_ones_attn", torch.ones(linear_hidden_dim * num_heads), persistent=False)
+        self.register_buffer("_zeros_attn", torch.zeros(linear_hidden_dim * num_heads), persistent=False)
+
+    def forward(
+        self,
+        x: torch.Tensor,
+        x_offsets: torch.Tensor,
+        all_timestamps: Optional[torch.Tensor],
+        invalid_attn_mask: torch.Tensor,
+        delta_x_offsets: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+        cache=None,
+        return_cache_states: bool = False,
+    ):
+        """x [sum_i N_i, D]; x_offsets [B + 1]; all_timestamps [B, n] int64 or None; invalid_attn_mask [n, n] (or [B, n, n])
+        -- only its size is used: the kernel applies the causal (lower-triangular) mask the reference builds (hstu.py:626-638).
+        Returns (x', (v, None, None, x')) like the reference (padded q / k are never materialised)."""
+        if delta_x_offsets is not None or cache is not None:
+            raise NotImplementedError("incremental (cached) research forward is not built; use modules.stu.STULayer.cached_forward")
+        kern = self.hammer_kernel()
+        if kern != HammerKernel.CUDA:
+            raise RuntimeError(f"generative_recommenders_b200 only implements HammerKernel.CUDA (got {kern})")
+        n = invalid_attn_mask.size(-1)
+        H, dqk, dv = self._num_heads, self._attention_dim, self._linear_dim
+        L = x.shape[0]
+        normed_x = layer_norm(x, self._ones_in, self._zeros_in, self._eps, kernel=kern)
+        mm = _SiluFunction.apply(torch.mm(normed_x, self._uvqk.to(x.dtype)))
+        u, v, q, k = torch.split(mm, [dv * H, dv * H, dqk * H, dqk * H], dim=1)
+        rb = self._rel_attn_bias
+        attn = hstu_rel_bias_attention(
+            n, q.reshape(L, H, dqk).contiguous(), k.reshape(L, H, dqk).contiguous(), v.reshape(L, H, dv).contiguous(), x_offsets,
+            rb._pos_w, rb._ts_w if all_timestamps is not None else None, all_timestamps,
+        ).reshape(L, H * dv)
+        residual = x + self._o.bias.to(x.dtype)
+        if self._concat_ua:
+            a = layer_norm(attn, self._ones_attn, self._zeros_attn, self._eps, kernel=kern)
+            u = u.contiguous()
+            o_input = torch.cat([u, a, u * a], dim=-1)
+            o_input = torch.nn.functional.dropout(o_input, p=self._dropout_ratio, training=self.training)
+            out = torch.addmm(residual, o_input, self._o.weight.to(x.dtype).t())
+        else:
+            # u * LN(attn) -> dropout -> x + y W_o: exactly the fused output stage of the STU block
+            out = hstu_compute_output(
+                attn=attn, u=u.contiguous(), x=residual, norm_weight=self._ones_attn, norm_bias=self._zeros_attn, norm_eps=self._eps,
+                output_weight=self._o.weight.t(), num_heads=H, linear_dim=dv, dropout_ratio=self._dropout_ratio,
+                training=self.training, concat_ux=False, group_norm=False, recompute_y_in_backward=False, kernel=kern,
+            )
+        return out, (v, None, None, out)

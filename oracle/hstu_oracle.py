@@ -516,3 +516,36 @@ def storage_quantisation(ref: torch.Tensor, dtype: torch.dtype) -> float:
     if dtype == torch.float32:
         return 0.0
     return rel_l2(ref.to(dtype).to(torch.float32), ref)
+
+
+def research_block_fwd(
+    x: torch.Tensor,
+    seq_offsets: torch.Tensor,
+    timestamps: Optional[torch.Tensor],
+    uvqk: torch.Tensor,
+    o_weight: torch.Tensor,
+    o_bias: torch.Tensor,
+    pos_w: torch.Tensor,
+    ts_w: Optional[torch.Tensor],
+    n: int,
+    num_heads: int,
+    attention_dim: int,
+    linear_dim: int,
+    concat_ua: bool = False,
+    eps: float = 1e-6,
+) -> torch.Tensor:
+    """SequentialTransductionUnitJagged.forward, "rel_bias" normalisation, silu activation, no cache, dropout 0
+    (research/modeling/sequential/hstu.py:318-436): LN without affine (:276-277) -> mm (no bias) -> SiLU on ALL of uvqk
+    (:322-323) -> split u|v|q|k (:326-335) -> rel-bias attention (:343-357) -> u * LN(attn) or cat[u, a, u*a] with
+    a = LN(attn) (:418-422) -> Linear(+bias) + x (:424-433).  Differentiable (torch ops only)."""
+    H, dqk, dv = num_heads, attention_dim, linear_dim
+    dt = x.dtype
+    normed = torch.nn.functional.layer_norm(x, [x.shape[1]], eps=eps)
+    mm = torch.nn.functional.silu(torch.mm(normed, uvqk))
+    u, v, q, k = torch.split(mm, [dv * H, dv * H, dqk * H, dqk * H], dim=1)
+    L = x.shape[0]
+    attn = hstu_rel_bias_attention_fwd(n, q.reshape(L, H, dqk), k.reshape(L, H, dqk), v.reshape(L, H, dv), seq_offsets,
+                                       pos_w, ts_w, timestamps, dtype=dt).reshape(L, H * dv)
+    a = torch.nn.functional.layer_norm(attn, [H * dv], eps=eps)
+    o_in = torch.cat([u, a, u * a], dim=-1) if concat_ua else u * a
+    return torch.nn.functional.linear(o_in, o_weight, o_bias) + x

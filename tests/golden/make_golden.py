@@ -234,6 +234,44 @@ def research_case(seed, B, H, n, dqk, dv):
                     dts_w=mod._ts_w.grad), os.path.join(HERE, "research_attn.pt"))
 
 
+def research_block_case(name, seed, B, D, H, n, dqk, dv, concat_ua):
+    """research/modeling/sequential/hstu.py:226-444 (SequentialTransductionUnitJagged.forward, no cache, eval-free: dropout 0)."""
+    from generative_recommenders.research.modeling.sequential.hstu import (
+        RelativeBucketedTimeAndPositionBasedBias,
+        SequentialTransductionUnitJagged,
+    )
+
+    torch.manual_seed(seed)
+    lengths = torch.randint(1, n + 1, (B,))
+    off = offsets_from(lengths.tolist())
+    L = int(off[-1])
+    x = torch.randn(L, D).requires_grad_()
+    ts = torch.cumsum(torch.randint(0, 5000, (B, n)), dim=1)
+    bias_mod = RelativeBucketedTimeAndPositionBasedBias(
+        max_seq_len=n, num_buckets=128,
+        bucketization_fn=lambda t: (torch.log(torch.abs(t).clamp(min=1)) / 0.301).long(),
+    )
+    with torch.no_grad():
+        bias_mod._ts_w.normal_(0, 0.02)
+        bias_mod._pos_w.normal_(0, 0.02)
+    blk = SequentialTransductionUnitJagged(
+        embedding_dim=D, linear_hidden_dim=dv, attention_dim=dqk, dropout_ratio=0.0, attn_dropout_ratio=0.0, num_heads=H,
+        linear_activation="silu", relative_attention_bias_module=bias_mod, normalization="rel_bias", linear_config="uvqk",
+        concat_ua=concat_ua, epsilon=1e-6, max_length=n,
+    )
+    with torch.no_grad():
+        blk._uvqk.normal_(0, 0.1)
+        blk._o.bias.normal_(0, 0.1)
+    invalid = torch.tril(torch.ones(n, n))
+    y, _ = blk(x, off, ts, invalid)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    torch.save(dict(n=n, H=H, D=D, dqk=dqk, dv=dv, concat_ua=concat_ua, eps=1e-6, x=x.detach(), seq_offsets=off, timestamps=ts,
+                    state_dict={k: v.detach().clone() for k, v in blk.state_dict().items()}, dy=dy, y=y.detach(), dx=x.grad,
+                    grads={k: p_.grad.detach().clone() for k, p_ in blk.named_parameters()}),
+               os.path.join(HERE, f"research_block_{name}.pt"))
+
+
 def main():
     f32, bf16 = torch.float32, torch.bfloat16
     #          name        seed B  H  uih tgt dqk dv  targets  mal ctx min_full dtype
@@ -256,6 +294,8 @@ def main():
     stu_case("gn_ctx_window", 42, 4, 48, 4, 8, 16, 2, 40, 6, True, 3, 9)
     jagged_case(51, 6, 8, 9, 12, 2)
     research_case(61, 3, 2, 24, 16, 16)
+    research_block_case("plain", 71, 3, 32, 2, 24, 16, 16, False)
+    research_block_case("concat_ua", 72, 4, 48, 4, 20, 8, 16, True)
     print("golden vectors written to", HERE)
 
 

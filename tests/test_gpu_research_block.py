@@ -1,0 +1,62 @@
+"""GPU parity of the research-path block against golden vectors produced by the UNMODIFIED
+reference module `SequentialTransductionUnitJagged` (research/modeling/sequential/hstu.py:226-444; fixtures
+tests/golden/research_block_*.pt written by tests/golden/make_golden.py): output, input gradient and every parameter
+gradient, fp32 (tolerance: rel-L2 <= 2e-5, tests/util.py; the two bias tables accumulate many tiny terms: 1e-4)."""
+import pytest
+import torch
+
+from conftest import golden
+from util import assert_rel
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _build(g):
+    from generative_recommenders_b200.modules.research_hstu import (
+        RelativeBucketedTimeAndPositionBasedBias,
+        SequentialTransductionUnitJagged,
+    )
+
+    blk = SequentialTransductionUnitJagged(
+        embedding_dim=g["D"], linear_hidden_dim=g["dv"], attention_dim=g["dqk"], dropout_ratio=0.0, attn_dropout_ratio=0.0,
+        num_heads=g["H"], linear_activation="silu",
+        relative_attention_bias_module=RelativeBucketedTimeAndPositionBasedBias(max_seq_len=g["n"], num_buckets=128),
+        normalization="rel_bias", linear_config="uvqk", concat_ua=g["concat_ua"], epsilon=g["eps"], max_length=g["n"],
+    )
+    blk.load_state_dict(g["state_dict"], strict=True)  # the reference's own state dict
+    return blk.to(DEV)
+
+
+@pytest.mark.parametrize("name", ["plain", "concat_ua"])
+def test_research_block_golden(name):
+    g = golden(f"research_block_{name}.pt")
+    blk = _build(g)
+    x = g["x"].to(DEV).requires_grad_()
+    n = g["n"]
+    y, cache = blk(x, g["seq_offsets"].to(DEV), g["timestamps"].to(DEV), torch.tril(torch.ones(n, n, device=DEV)))
+    y.backward(g["dy"].to(DEV))
+    assert_rel(y, g["y"], f"research block {name} y")
+    assert_rel(x.grad, g["dx"], f"research block {name} dx")
+    for k, ref in g["grads"].items():
+        got = dict(blk.named_parameters())[k].grad
+        assert got is not None, k
+        assert_rel(got, ref, f"research block {name} d{k}", tol=1e-4 if "_rel_attn_bias" in k else None)
+    assert cache[3] is y
+
+
+def test_research_block_dropout_and_eval_are_consistent():
+    """training with p > 0 drops ~p of the output-stage activations (statistically), eval is deterministic."""
+    g = golden("research_block_plain.pt")
+    blk = _build(g)
+    blk._dropout_ratio = 0.5
+    x = g["x"].to(DEV)
+    n = g["n"]
+    args = (x, g["seq_offsets"].to(DEV), g["timestamps"].to(DEV), torch.tril(torch.ones(n, n, device=DEV)))
+    blk.eval()
+    y0, _ = blk(*args)
+    y1, _ = blk(*args)
+    assert torch.equal(y0, y1)
+    blk.train()
+    yt, _ = blk(*args)
+    assert torch.isfinite(yt).all() and not torch.equal(yt, y0)

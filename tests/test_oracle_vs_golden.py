@@ -107,3 +107,20 @@ def test_research_rel_bias_attention():
                                         g["v"].view(-1, H, dv), g["seq_offsets"], g["pos_w"], g["ts_w"],
                                         g["timestamps"])
     assert O.rel_l2(out.reshape(-1, H * dv), g["out"]) <= F32_TOL
+
+
+@pytest.mark.parametrize("name", ["plain", "concat_ua"])
+def test_research_block(name):
+    """The research block restated in the oracle vs the unmodified reference module, fwd + every grad."""
+    g = golden(f"research_block_{name}.pt")
+    sd = g["state_dict"]
+    leaves = {k: sd[k].clone().requires_grad_() for k in sd}
+    x = g["x"].clone().requires_grad_()
+    y = O.research_block_fwd(x, g["seq_offsets"], g["timestamps"], leaves["_uvqk"], leaves["_o.weight"], leaves["_o.bias"],
+                             leaves["_rel_attn_bias._pos_w"], leaves["_rel_attn_bias._ts_w"], g["n"], g["H"], g["dqk"], g["dv"],
+                             g["concat_ua"], g["eps"])
+    assert O.rel_l2(y, g["y"]) < 2e-6
+    y.backward(g["dy"])
+    assert O.rel_l2(x.grad, g["dx"]) < 2e-6
+    for k, ref in g["grads"].items():
+        assert O.rel_l2(leaves[k].grad, ref) < 5e-6, k

@@ -1,0 +1,56 @@
+"""Host-side checks of the research-path block that need no GPU: the reference's state dict loads unchanged, unsupported
+options fail loudly, and there is no CPU fallback."""
+import pytest
+import torch
+
+from conftest import golden
+
+
+def _mk(**kw):
+    from generative_recommenders_b200.modules.research_hstu import (
+        RelativeBucketedTimeAndPositionBasedBias,
+        SequentialTransductionUnitJagged,
+    )
+
+    args = dict(embedding_dim=32, linear_hidden_dim=16, attention_dim=16, dropout_ratio=0.0, attn_dropout_ratio=0.0, num_heads=2,
+                linear_activation="silu", relative_attention_bias_module=RelativeBucketedTimeAndPositionBasedBias(24, 128),
+                normalization="rel_bias", linear_config="uvqk", concat_ua=False, epsilon=1e-6, max_length=24)
+    args.update(kw)
+    return SequentialTransductionUnitJagged(**args)
+
+
+@pytest.mark.parametrize("name", ["plain", "concat_ua"])
+def test_reference_state_dict_loads_strictly(name):
+    g = golden(f"research_block_{name}.pt")
+    from generative_recommenders_b200.modules.research_hstu import RelativeBucketedTimeAndPositionBasedBias
+
+    blk = _mk(embedding_dim=g["D"], linear_hidden_dim=g["dv"], attention_dim=g["dqk"], num_heads=g["H"], concat_ua=g["concat_ua"],
+              relative_attention_bias_module=RelativeBucketedTimeAndPositionBasedBias(g["n"], 128), max_length=g["n"])
+    missing, unexpected = blk.load_state_dict(g["state_dict"], strict=True)
+    assert not missing and not unexpected
+    assert set(blk.state_dict().keys()) == set(g["state_dict"].keys())
+    for k, v in g["state_dict"].items():
+        assert torch.equal(blk.state_dict()[k], v)
+
+
+def test_unsupported_options_raise():
+    with pytest.raises(ValueError):
+        _mk(linear_config="uv")
+    with pytest.raises(NotImplementedError):
+        _mk(normalization="softmax_rel_bias")
+    with pytest.raises(NotImplementedError):
+        _mk(linear_activation="none")
+    with pytest.raises(ValueError):
+        _mk(relative_attention_bias_module=None)
+    with pytest.raises(NotImplementedError):
+        _mk(attn_dropout_ratio=0.1)
+
+
+def test_no_cpu_fallback():
+    blk = _mk()
+    x = torch.randn(10, 32)
+    off = torch.tensor([0, 4, 10])
+    with pytest.raises(RuntimeError):
+        blk(x, off, None, torch.tril(torch.ones(24, 24)))
+    with pytest.raises(NotImplementedError):
+        blk(x, off, None, torch.tril(torch.ones(24, 24)), delta_x_offsets=(off, off), cache=(None,) * 4)
