@@ -373,73 +373,6 @@ __global__ void __launch_bounds__(128) umma_multi_kernel(int nissuers, int group
 }
 
 
-// ---- does the tensor pipe pay for switching between MMA kinds?  One thread issues runs of `run` MMAs of kind P followed by
-// `run` MMAs of kind Q (different shape / operand source / major-ness), 2048 MMAs in total. ----
-//   kind 0: SS  N=64  A K-major SW128, B K-major SW128        kind 1: SS  N=32  A K-major SW128, B MN-major SW64
-//   kind 2: TS  N=32  A TMEM,          B MN-major SW64        kind 3: SS  N=32  A MN-major SW128, B MN-major SW64
-//   kind 4: SS  N=32  A K-major SW128, B K-major SW128
-__global__ void __launch_bounds__(128) umma_switch_kernel(int kind_p, int kind_q, int run, long long* out) {
-  extern __shared__ __align__(1024) uint8_t smem_raw5[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw5) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar;
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
-  if (tid == 0) {
-    mbar_init(&bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
-  fence_proxy_async_smem();
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {
-    const uint32_t sa = smem_u32(smem), sb = smem_u32(smem) + 32768;
-    const uint64_t a_k = desc_kmajor<128>(sa, 0), a_mn = desc_mnmajor<128>(sa, 0, 16384);
-    const uint64_t b_k = desc_kmajor<128>(sb, 0), b_mn = desc_mnmajor<64>(sb, 0, 8192);
-    auto issue = [&](int kind, int j) {
-      const uint64_t o = (uint64_t)((j & 3) * 2);
-      switch (kind) {
-        case 0: mma_ss(tmem, a_k + o, b_k + o, make_idesc(128, 64, false, false, true, true), 1); break;
-        case 1: mma_ss(tmem + 64, a_k + o, b_mn + o * 0, make_idesc(128, 32, false, true, true, true), 1); break;
-        case 2: mma_ts(tmem + 128, tmem + 448, b_mn, make_idesc(128, 32, false, true, true, true), 1); break;
-        case 3: mma_ss(tmem + 192, a_mn, b_mn, make_idesc(128, 32, true, true, true, true), 1); break;
-        default: mma_ss(tmem + 256, a_k + o, b_k + o, make_idesc(128, 32, false, false, true, true), 1); break;
-      }
-    };
-    const int count = 2048;
-    long long t0 = clock64();
-    for (int i = 0; i < count; i += 2 * run) {
-      for (int j = 0; j < run; ++j) issue(kind_p, j);
-      for (int j = 0; j < run; ++j) issue(kind_q, j);
-    }
-    mma_commit(&bar);
-    mbar_wait(&bar, 0);
-    long long t1 = clock64();
-    out[0] = t1 - t0;
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
-static void switch_case(int kp, int kq, int run, char* report, size_t cap) {
-  long long* d = nullptr;
-  long long h[1] = {0};
-  cudaMalloc(&d, sizeof(h));
-  cudaFuncSetAttribute(umma_switch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560);
-  umma_switch_kernel<<<1, 128, 66560>>>(kp, kq, run, d);
-  if (cudaDeviceSynchronize() != cudaSuccess) {
-    rep(report, cap, "mma-switch/ CUDA-ERROR\n");
-    return;
-  }
-  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-  cudaFree(d);
-  rep(report, cap, "mma-switch/kind %d x%d then kind %d x%d: %6.1f clk per MMA\n", kp, run, kq, run, (double)h[0] / 2048.0);
-}
-
 static void multi_case(int nissuers, int wait_each, char* report, size_t cap) {
   long long* d = nullptr;
   long long h[1] = {0};
@@ -626,11 +559,7 @@ int umma_selftest(char* report, size_t cap) {
   commit_case(2, 2, report, cap);
   for (int w = 0; w < 2; ++w)
     for (int n = 1; n <= 3; ++n) multi_case(n, w, report, cap);
-  {
-    const int pairs[][2] = {{0, 0}, {1, 1}, {2, 2}, {3, 3}, {4, 4}, {0, 1}, {0, 2}, {1, 2}, {1, 3}, {0, 4}, {4, 1}, {4, 2}};
-    for (auto& pq : pairs)
-      for (int run : {1, 4, 8}) switch_case(pq[0], pq[1], run, report, cap);
-  }
+
   mufu_case<0>("tanh.approx.f32", 4, report, cap);
   mufu_case<1>("ex2+rcp f32 (sigmoid)", 2, report, cap);
   mufu_case<2>("tanh.approx.bf16x2", 4, report, cap);
