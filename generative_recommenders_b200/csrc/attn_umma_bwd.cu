@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     // Work is pipelined in "units" u = 2 i + h: half h (64 query rows) of query tile i.  Unit u's scores live in TMEM
     // slot u % NSLOT; warpgroup h turns them into P^T (bf16, over the front of the slot) and the dS^T box (pair i & 1,
     // box h) in shared memory.  Three threads issue, each with its own wait -> issue -> commit loop: measured
-    // (umma_selftest mma-multi), one thread that commits after 8 MMAs reaches 71 clk / MMA, two or three threads 40,
+    // (umma_selftest mma-multi), one thread that commits after 8 MMAs reaches 71-84 clk / MMA, two threads 41-47, three 40,
     // because tcgen05.commit and the barrier waits stall only their own issuer.
     //   X (this warp): S^T, dP^T of every unit.     Y (warp 2): dV, dK of every unit.     Z (warp 3): dQ of every tile.
     // The whole warp runs the warp-uniform control flow, one fixed lane issues; descriptors are built once.

@@ -9,7 +9,7 @@
 //   warp 2         : TMEM allocation / release; lane 0 = issuer 2:  O += P_t V_t  (TS: A = P_t read from the front of
 //                    slot t % 3, B = V_t MN-major), rotating over NACC accumulators, one commit per tile.
 //                    Two issuing threads because tcgen05.commit and the barrier waits stall only their own issuer
-//                    (umma_selftest: one thread 71 clk / MMA, two threads 40).
+//                    (umma_selftest: one thread 71-84 clk / MMA, two threads 41-47).
 //   warps 4-7, 8-11: two "silu" warpgroups.  Warpgroup g owns key tiles t = g, g+2, ...: tcgen05.ld S (one query row per
 //                    thread, next 32 columns prefetched), p = silu(alpha*s) * mask via one MUFU (tanh) + packed fp32x2
 //                    FMUL2 / FFMA2, packs bf16 pairs and writes them with tcgen05.st over the S columns already read.
