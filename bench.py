@@ -166,7 +166,10 @@ def run_ours(args):
         dist.barrier()
     _lib.lib()
     D, H, dh, layers = 256, 8, 32, args.layers
-    lengths, nt, off = synth_lengths(args.batch, args.lmax, dev, 1001 + rank)
+    # the same seeded lengths on every rank (weak scaling: identical sum of len^2 per GPU, so the curve measures the collective
+    # and not a straggler); the activations / gradients differ per rank (seeded below)
+    lengths, nt, off = synth_lengths(args.batch, args.lmax, dev, 1001)
+    torch.cuda.manual_seed(4321 + rank)  # dropout masks: CUDA generator, different per rank
     L = int(off[-1])
 
     if args.workload == "hstu_large":
@@ -177,6 +180,7 @@ def run_ours(args):
                           for _ in range(layers)]).to(dev).to(torch.bfloat16)
         params = [p for p in stack.parameters()]
         opt = torch.optim.AdamW(params, lr=1e-4, fused=True)
+        torch.manual_seed(100 + rank)
         x_dev = torch.randn(L, D, device=dev, dtype=torch.bfloat16)
         # e2e: the step's inputs live in pinned host memory and are copied in every step
         x_host = x_dev.cpu().pin_memory()
@@ -184,8 +188,9 @@ def run_ours(args):
         h2d_bytes = x_host.numel() * 2 + off_host.numel() * 8 + nt_host.numel() * 4 + len_host.numel() * 4
         from generative_recommenders_b200.distributed import LayerBucketAllReduce
 
-        # one flat NCCL all-reduce per STU layer, launched as soon as that layer's grads are final (side stream)
-        reducer = LayerBucketAllReduce(list(stack._stu_layers), world, dev) if world > 1 else None
+        # gradients live in one flat bf16 buffer (p.grad are views); for N > 1 one in-place NCCL all-reduce (AVG) per STU layer
+        # is launched on a side stream as soon as that layer's grads are final.  Same code path at N = 1 (no collective).
+        reducer = LayerBucketAllReduce(list(stack._stu_layers), world, dev)
 
         def step(e2e: bool):
             if e2e:
@@ -195,12 +200,11 @@ def run_ours(args):
                 l_ = len_host.to(dev, non_blocking=True)
             else:
                 x, o_, n_, l_ = x_dev, off, nt, lengths
-            opt.zero_grad(set_to_none=True)
+            reducer.zero_grad()
             y = stack(x=x, x_lengths=l_, x_offsets=o_, max_seq_len=args.lmax, num_targets=n_)
             loss = y.float().square().mean()
             loss.backward()
-            if reducer is not None:
-                reducer.wait()
+            reducer.wait()
             opt.step()
             if e2e:
                 return float(loss.item())  # device -> host read of the step result
@@ -209,9 +213,9 @@ def run_ours(args):
         units_per_step = args.batch
         d2h_bytes = 4
         cfg = {"workload": f"HSTU-large stack fwd+bwd+AdamW: {layers} layers, D=256, H=8, dqk=dv=32, bf16, Lmax={args.lmax}, "
-                           f"{args.batch} user sequences/GPU (lengths U[0.9,1.0)*Lmax, 1-20 targets, seed 1001+rank), dropout 0.2",
+                           f"{args.batch} user sequences/GPU (lengths U[0.9,1.0)*Lmax, 1-20 targets, seed 1001 on every rank; activations seeded per rank), dropout 0.2",
                "global_batch": args.batch * world, "seq_len": args.lmax, "rows_per_gpu": L,
-               "parallelism": f"dp{world} (batch-sharded, per-layer NCCL all-reduce of grads overlapped with backward)",
+               "parallelism": f"dp{world} (batch-sharded, per-layer in-place bf16 NCCL all-reduce of the flat gradient bucket overlapped with backward)",
                "l2": f"inputs + activations per step ({L * D * 2 * 6 / 1e6:.0f} MB+) exceed the 126 MB L2; no explicit flush"}
         cfg["attn_shape"] = {"batch": args.batch, "lmax": args.lmax, "heads": H, "d": dh}
         aflops = attn_flops(lengths, H, dh, dh)

@@ -38,6 +38,7 @@ struct SeqGeom {
   long long kv_row0;  // first memory row of this sequence in k/v
   long long q_row0;   // first memory row of this sequence's query rows in q/out
   int len;            // number of key positions (clipped to max_seq_len)
+  int len_true;       // unclipped length (rows [len, len_true) of a full-attention call are zero-filled)
   int q_pos0;         // sequence position of the first query row
   int nq;             // number of query rows
   int n_tgt;          // -1 if none
@@ -49,6 +50,7 @@ __device__ __forceinline__ SeqGeom seq_geom(const hstu_attn_params& p, int b) {
   long long e = load_index(p.seq_offsets, p.offsets_are_i64, b + 1);
   int len = (int)(e - s);
   g.kv_row0 = s;
+  g.len_true = len;
   g.n_tgt = p.num_targets ? (int)load_index(p.num_targets, p.num_targets_are_i64, b) : -1;
   if (p.delta_q_len > 0) {
     // pytorch_cached_hstu_mha (pt_hstu_attention.py:175-235): queries are the last delta rows; keys are not clipped
@@ -90,6 +92,8 @@ __global__ void __launch_bounds__(256) attn_fwd_generic_kernel(const GenericArgs
   const SeqGeom g = seq_geom(p, b);
   const int mt = gridDim.x - 1 - blockIdx.x;  // heavy (late) tiles first
   const int m0 = mt * TILE;
+  if (blockIdx.x == 0 && p.delta_q_len == 0 && g.len_true > g.len)
+    zero_rows(p.out, sizeof(T), p.o_row_stride, (long long)h * p.o_head_stride, p.dv, g.kv_row0 + g.len, g.kv_row0 + g.len_true);
   if (m0 >= g.nq) return;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int dqk = p.dqk, dv = p.dv;
@@ -194,6 +198,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kv_generic_kernel(const GenericA
   const int b = blockIdx.z, h = blockIdx.y;
   const SeqGeom g = seq_geom(p, b);
   const int n0 = blockIdx.x * TILE;  // early key tiles are the heavy ones and come first
+  if (blockIdx.x == 0 && g.len_true > g.len) {
+    zero_rows(p.dk, sizeof(T), p.dk_row_stride, (long long)h * p.dk_head_stride, p.dqk, g.kv_row0 + g.len, g.kv_row0 + g.len_true);
+    zero_rows(p.dv_out, sizeof(T), p.dv_row_stride, (long long)h * p.dv_head_stride, p.dv, g.kv_row0 + g.len, g.kv_row0 + g.len_true);
+  }
   if (n0 >= g.len) return;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int dqk = p.dqk, dv = p.dv;
@@ -335,6 +343,8 @@ __global__ void __launch_bounds__(256) attn_bwd_q_generic_kernel(const GenericAr
   const SeqGeom g = seq_geom(p, b);
   const int mt = gridDim.x - 1 - blockIdx.x;
   const int m0 = mt * TILE;
+  if (blockIdx.x == 0 && g.len_true > g.len)
+    zero_rows(p.dq, sizeof(T), p.dq_row_stride, (long long)h * p.dq_head_stride, p.dqk, g.kv_row0 + g.len, g.kv_row0 + g.len_true);
   if (m0 >= g.len) return;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int dqk = p.dqk, dv = p.dv;

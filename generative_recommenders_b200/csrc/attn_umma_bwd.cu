@@ -10,8 +10,12 @@
 //   key row per thread) turn S^T, dP^T into
 //        P^T  = silu(alpha S)            * mask      (1/N folded into the dV epilogue)
 //        dS^T = dP sig (1 + x (1 - sig)) * mask      (alpha/N folded into the dK epilogue / dQ convert)
-//   from ONE tanh per score (packed fp32x2 arithmetic).  P^T (bf16) overwrites the front of the slot in TMEM, dS^T goes to a
-//   bf16 box in shared memory ([kv][q], q contiguous, 128B swizzle; two box pairs).
+//   from ONE tanh per score (packed fp32x2 arithmetic).  Both are ALWAYS fp16 tensor-core operands, whatever the input dtype
+//   (kind::f16 takes the A and B formats independently): an 11-bit significand keeps their rounding inside the 1e-3 parity
+//   budget, a bf16 P / dS does not (measured 1.7e-3).  P is bounded by |alpha s|; dS inherits the scale of dO, so it is stored
+//   as dS * 2^-e with e = floor(log2 max|dO|) (dout_amax_kernel) and the power of two is undone in the epilogues.
+//   P^T overwrites the front of the slot in TMEM, dS^T goes to a box in shared memory ([kv][q], q contiguous, 128B swizzle;
+//   two box pairs).
 //   Y:  dV  += P^T  dO        (A = P^T from the TMEM slot,  B = 64 rows of dO_i MN-major)   [kv x d]  all query tiles
 //   Z:  dK  += dS^T Q         (A = dS^T box K-major,  B = 64 rows of Q_i  MN-major)         [kv x d]
 //       dQ_i = dS   K         (A = both dS^T boxes of the tile read MN-major, B = K MN-major)   [128 q x d]
@@ -21,6 +25,8 @@
 //
 // Reference math: ops/triton/triton_hstu_attention.py:995-1006,1222 and SURVEY.md appendix A; unlike the Triton
 // kernel dQ is accumulated in fp32, not in the input dtype (triton_attention_utils.py:47-60).
+#include <string.h>
+
 #include "common.cuh"
 #include "internal.h"
 #include "umma.cuh"
@@ -37,6 +43,7 @@ struct alignas(64) BwdParams {
   void* dk;
   void* dv;
   float* dq_acc;  // [L, H, D] fp32, zero-initialised
+  const uint32_t* dout_amax_bits;  // fp32 bit pattern of max |dO| over the whole tensor (written by dout_amax_kernel)
   long long dk_row_stride, dk_head_stride, dv_row_stride, dv_head_stride;
   int offsets_i64, targets_i64;
   int max_seq_len, heads;
@@ -117,6 +124,48 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// 2^-e with e = floor(log2(amax)) (amax given as fp32 bits): amax * scale lies in [1, 2).  Zero / denormal / non-finite amax
+// are clamped to the representable exponent range, so the result is always a finite, non-zero power of two.
+__host__ __device__ __forceinline__ float ds_scale_from_amax(uint32_t amax_bits) {
+  uint32_t e = (amax_bits >> 23) & 0xffu;
+  e = e < 1u ? 127u : (e > 253u ? 253u : e);  // amax == 0 -> scale 1
+  const uint32_t bits = (254u - e) << 23;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(bits);
+#else
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+#endif
+}
+
+// max |dO| over the [rows, heads, D] tensor -> atomicMax on the fp32 bit pattern (order-preserving for non-negative floats)
+template <bool BF16>
+__global__ void dout_amax_kernel(const uint16_t* __restrict__ dout, long long rows, int heads, int D, long long row_stride,
+                                 long long head_stride, uint32_t* __restrict__ amax_bits) {
+  const long long nvec = rows * heads * (D / 8);
+  uint32_t m = 0;  // max of the 15-bit magnitudes (monotone in |x| for both 16-bit formats)
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % (D / 8));
+    const long long rh = idx / (D / 8);
+    const int hh = (int)(rh % heads);
+    const long long r = rh / heads;
+    const uint4 x = *reinterpret_cast<const uint4*>(dout + r * row_stride + hh * head_stride + v * 8);
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      m = max(m, w[i] & 0x7fffu);
+      m = max(m, (w[i] >> 16) & 0x7fffu);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m != 0) {
+    const uint32_t fbits = BF16 ? (m << 16) : __float_as_uint(__half2float(__ushort_as_half((unsigned short)m)));
+    atomicMax(amax_bits, fbits);
+  }
+}
+
 template <int D, bool BF16>
 __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = BwdCfg<D>;
@@ -126,7 +175,13 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
   const int n0 = (int)blockIdx.x * 128;
   const long long row0 = load_index(p.seq_offsets, p.offsets_i64, b);
   int len = (int)(load_index(p.seq_offsets, p.offsets_i64, b + 1) - row0);
-  len = len < p.max_seq_len ? len : p.max_seq_len;
+  if (len > p.max_seq_len) {  // rows past max_seq_len: zero gradients (dq: the accumulator stays zero there)
+    if (blockIdx.x == 0) {
+      zero_rows(p.dk, 2, p.dk_row_stride, (long long)h * p.dk_head_stride, D, row0 + p.max_seq_len, row0 + len);
+      zero_rows(p.dv, 2, p.dv_row_stride, (long long)h * p.dv_head_stride, D, row0 + p.max_seq_len, row0 + len);
+    }
+    len = p.max_seq_len;
+  }
   if (n0 >= len) return;
   const int n_tgt = p.num_targets ? (int)load_index(p.num_targets, p.targets_i64, b) : -1;
   const SeqMask msk = make_seq_mask(len, n_tgt, p.win, p.min_full, p.ctx);
@@ -251,7 +306,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     // ---- issuer Y: dV += P^T dO (A = P^T from the unit's TMEM slot) and dK += dS^T Q (A = the dS^T box) of every unit ----
     constexpr int NSLOT = Cfg::NSLOT;
     const bool leader = lane == 0;
-    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // A K-major, B MN-major
+    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, false, BF16);    // A (P^T / dS^T: always fp16) K-major, B MN-major
     const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box [kv][q] as K-major A (dK)
     const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
     const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
@@ -287,7 +342,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
   } else if (warp == 3) {
     // ---- issuer Z: dQ_i = dS_i K (A = the dS^T box pair read MN-major, M = 128 query rows) of every query tile ----
     const bool leader = lane == 0;
-    constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // A MN-major, B MN-major
+    constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, false, BF16);     // A (dS^T: fp16) MN-major, B MN-major
     const uint64_t dds_mn = desc_mnmajor<128>(smem_u32(sDST), 0, 16384);           // the box pair as MN-major A
     const uint64_t dk_mn = desc_mnmajor<SW>(smem_u32(sK), 0, Cfg::BOX_BYTES);      // K as MN-major B
     for (int i = 0; i < T; ++i) {
@@ -317,7 +372,11 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
     const int j_pos = n0 + row;
     const float2 ah2 = make_float2(p.alpha_half, p.alpha_half);
-    const float2 half2v = make_float2(0.5f, 0.5f), nhalf2v = make_float2(-0.5f, -0.5f);
+    // dS^T is an fp16 tensor-core operand (see the header comment): it is stored as dS * 2^-e with e = floor(log2 max|dO|),
+    // the power of two is folded into the constants of the sigmoid-derivative polynomial, and removed again in the dK epilogue
+    // and in dq_convert_kernel.
+    const float ds_scale = ds_scale_from_amax(__ldg(p.dout_amax_bits));
+    const float2 shalf2v = make_float2(0.5f * ds_scale, 0.5f * ds_scale), nshalf2v = make_float2(-0.5f * ds_scale, -0.5f * ds_scale);
     const bool fast = msk.fast != 0;
     const bool j_ok = j_pos < len;
     const bool j_hist = j_ok && (!msk.has_tgt || j_pos < msk.max_id);  // fast mask: valid = (j_hist & i > j) | (i == j)
@@ -398,8 +457,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[E]), __uint_as_float(s[E + 1])), ah2);          \
     const float2 t = make_float2(tanh_approx(hh.x), tanh_approx(hh.y));                                        \
     const float2 pv = __ffma2_rn(hh, t, hh);                                                                   \
-    const float2 sig = __ffma2_rn(half2v, t, half2v);                                                          \
-    const float2 onem = __ffma2_rn(nhalf2v, t, half2v);                                                        \
+    const float2 sig = __ffma2_rn(shalf2v, t, shalf2v);   /* scale * sig        */                             \
+    const float2 onem = __ffma2_rn(nshalf2v, t, shalf2v); /* scale * (1 - sig)  */                             \
     const float2 dv = __fmul2_rn(make_float2(__uint_as_float(dp[E]), __uint_as_float(dp[E + 1])),              \
                                  __ffma2_rn(pv, onem, sig));                                                   \
     P0 = pv.x; P1 = pv.y; D0 = dv.x; D1 = dv.y;                                                                \
@@ -409,8 +468,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
           for (int e = 0; e < 32; e += 2) {
             float p0, p1, d0, d1;
             HSTU_BWD_ELEM2(e, p0, p1, d0, d1);
-            pp[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
-            dd[e >> 1] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
+            pp[e >> 1] = pack_f16x2_sat(p0, p1);
+            dd[e >> 1] = pack_f16x2_sat(d0, d1);
           }
         } else if (mode == 1) {
           // valid(i, j) = ((j is history) & (i > j)) | (i == j), restricted to i < len and j < len
@@ -425,8 +484,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
             const bool v1 = ((c0 + 1 > lo_c) | (c0 + 1 == dg_c)) & (c0 + 1 < len_rel);
             p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;
             p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;
-            pp[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
-            dd[e >> 1] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
+            pp[e >> 1] = pack_f16x2_sat(p0, p1);
+            dd[e >> 1] = pack_f16x2_sat(d0, d1);
           }
         } else {
 #pragma unroll
@@ -438,8 +497,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
             const bool v1 = j_ok && i_pos + 1 < len && mask_valid(msk, i_pos + 1, j_pos);
             p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;
             p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;
-            pp[e >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
-            dd[e >> 1] = BF16 ? pack_bf16x2(d0, d1) : pack_f16x2(d0, d1);
+            pp[e >> 1] = pack_f16x2_sat(p0, p1);
+            dd[e >> 1] = pack_f16x2_sat(d0, d1);
           }
         }
 #undef HSTU_BWD_ELEM2
@@ -465,7 +524,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     mbar_wait(&bars->fin_full, 0);
     tc_fence_after_sync();
     const uint32_t acc = tmem + (wg == 0 ? Cfg::TMEM_DV : Cfg::TMEM_DK) + lane_bits;
-    const float scale = wg == 0 ? p.dv_scale : p.dk_scale;
+    const float scale = wg == 0 ? p.dv_scale : p.dk_scale / ds_scale;  // ds_scale is a power of two: exact
     uint16_t* gptr = wg == 0
         ? reinterpret_cast<uint16_t*>(p.dv) + (row0 + j_pos) * p.dv_row_stride + (long long)h * p.dv_head_stride
         : reinterpret_cast<uint16_t*>(p.dk) + (row0 + j_pos) * p.dk_row_stride + (long long)h * p.dk_head_stride;
@@ -495,7 +554,9 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
 // dq[r, h, :] = convert(dq_acc[r, h, :] * scale)
 template <bool BF16>
 __global__ void dq_convert_kernel(const float* __restrict__ acc, uint16_t* __restrict__ dq, long long rows, int heads, int D,
-                                  long long row_stride, long long head_stride, float scale) {
+                                  long long row_stride, long long head_stride, float scale_in,
+                                  const uint32_t* __restrict__ amax_bits) {
+  const float scale = scale_in / ds_scale_from_amax(__ldg(amax_bits));  // dq_acc holds alpha-less, 2^-e scaled sums
   const long long nvec = rows * heads * (D / 8);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(idx % (D / 8));
@@ -541,7 +602,8 @@ bool umma_supported(const hstu_attn_params& p, bool bwd) {
 
 size_t umma_workspace_bytes(const hstu_attn_params& p, bool bwd) {
   if (!bwd) return 0;
-  return (size_t)p.total_rows * p.heads * p.dqk * sizeof(float);
+  // fp32 dQ accumulator [L, H, D] + one 256-byte slot for the max |dO| word
+  return (size_t)p.total_rows * p.heads * p.dqk * sizeof(float) + 256;
 }
 
 template <int D, bool BF16>
@@ -564,6 +626,8 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   bp.dk = p.dk;
   bp.dv = p.dv_out;
   bp.dq_acc = reinterpret_cast<float*>(p.workspace);
+  uint32_t* amax_bits = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.workspace) + (need - 256));
+  bp.dout_amax_bits = amax_bits;
   bp.dk_row_stride = p.dk_row_stride;
   bp.dk_head_stride = p.dk_head_stride;
   bp.dv_row_stride = p.dv_row_stride;
@@ -579,6 +643,12 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   bp.dv_scale = 1.0f / (float)p.max_seq_len;
   bp.dk_scale = p.alpha / (float)p.max_seq_len;
   HSTU_CUDA_OK(cudaMemsetAsync(p.workspace, 0, need, st));
+  const long long nvec = p.total_rows * p.heads * (D / 8);
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dout_amax_kernel<BF16><<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(p.dout), p.total_rows, p.heads, D,
+                                                      p.do_row_stride, p.do_head_stride, amax_bits);
+  HSTU_CUDA_OK(cudaGetLastError());
   auto kern = attn_bwd_umma_kernel<D, BF16>;
   HSTU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   dim3 grid((p.max_seq_len + 127) / 128, p.heads, p.batch);
@@ -610,11 +680,10 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
     cudaMemcpyToSymbol(g_trace, &tbuf, sizeof(tbuf));
   }
 #endif
-  const long long nvec = p.total_rows * p.heads * (D / 8);
-  long long blocks = (nvec + 255) / 256;
+  blocks = (nvec + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   dq_convert_kernel<BF16><<<(int)blocks, 256, 0, st>>>(bp.dq_acc, reinterpret_cast<uint16_t*>(p.dq), p.total_rows, p.heads, D,
-                                                       p.dq_row_stride, p.dq_head_stride, bp.dk_scale);
+                                                       p.dq_row_stride, p.dq_head_stride, bp.dk_scale, amax_bits);
   HSTU_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -162,6 +162,20 @@ __device__ __forceinline__ long long load_index(const void* p, int is_i64, int i
   return is_i64 ? (long long)reinterpret_cast<const long long*>(p)[idx] : (long long)reinterpret_cast<const int*>(p)[idx];
 }
 
+// Rows [r0, r1) of head `head_off` (element offset) of a [rows, heads, d] tensor := 0, by all threads of the CTA.  Used for the
+// rows of a sequence at positions >= max_seq_len: the reference drops them on the way in (jagged_to_padded_dense truncates)
+// and returns zeros for them (dense_to_jagged of the padded result), pt_hstu_attention.py:97-167.  Rare path: plain stores.
+__device__ __forceinline__ void zero_rows(void* base, int elem_bytes, long long row_stride, long long head_off, int d,
+                                          long long r0, long long r1) {
+  const long long n = (r1 - r0) * d;
+  for (long long idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const long long r = r0 + idx / d, c = idx % d;
+    const long long off = r * row_stride + head_off + c;
+    if (elem_bytes == 2) reinterpret_cast<uint16_t*>(base)[off] = 0;
+    else reinterpret_cast<uint32_t*>(base)[off] = 0u;
+  }
+}
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 

@@ -26,6 +26,7 @@ struct StCfg {
   int b_mode;  // 0 K-major TMA, 1 MN-major TMA
   int sw_a, sw_b;
   int variant;  // 1: swap LBO/SBO of MN-major descriptors (diagnostic)
+  int a_f16;    // 1: A holds fp16 values while B stays bf16 (mixed operand formats of kind::f16: the fp16 P / dS operands)
 };
 
 template <int SW>
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constan
   if (tid == 0) {
     mbar_wait(&bar_full, 0);
     tc_fence_after_sync();
-    const uint32_t idesc = make_idesc(M, N, cfg.a_mode == 1, cfg.b_mode == 1, true, true);
+    const uint32_t idesc = make_idesc(M, N, cfg.a_mode == 1, cfg.b_mode == 1, cfg.a_f16 == 0, true);
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
     for (int k = 0; k < K / 16; ++k) {
       const uint64_t bd = op_desc_rt(cfg.sw_b, cfg.b_mode, b_base, cfg.b_mode == 1 ? K : N, k, cfg.variant);
@@ -416,6 +417,12 @@ static int run_gemm_case(const char* name, StCfg cfg, char* report, size_t cap) 
   // device storage: K-major operands as [rows][K]; MN-major operands as [K][rows]
   std::vector<__nv_bfloat16> dAh = hA, dBh = hB;
   if (cfg.a_mode == 1) for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) dAh[(size_t)k * M + m] = hA[(size_t)m * K + k];
+  if (cfg.a_f16) {  // same values, fp16 bit patterns (the tensor map / copies only move 16-bit words)
+    for (auto& x : dAh) {
+      const __half hv = __float2half(__bfloat162float(x));
+      memcpy((void*)&x, &hv, 2);
+    }
+  }
   if (cfg.b_mode == 1) for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) dBh[(size_t)k * N + n] = hB[(size_t)n * K + k];
   __nv_bfloat16 *dA = nullptr, *dB = nullptr;
   float* dD = nullptr;
@@ -526,6 +533,13 @@ int umma_selftest(char* report, size_t cap) {
       {"A TMEM K128, B MN sw64 N32",      {32, 128, 3, 1, 128, 64, 0}},
       {"A TMEM K128, B MN sw128 N128",    {128, 128, 3, 1, 128, 128, 0}},
       {"A TMEM K64, B K sw128 N128",      {128, 64, 3, 0, 128, 128, 0}},
+      // mixed operand formats: A fp16 (P / dS of the attention kernels), B bf16
+      {"A f16 TMEM K128, B bf16 MN sw64",  {32, 128, 3, 1, 128, 64, 0, 1}},
+      {"A f16 TMEM K128, B bf16 MN sw128", {128, 128, 3, 1, 128, 128, 0, 1}},
+      {"A f16 manual K128, B bf16 MN sw64", {32, 128, 2, 1, 128, 64, 0, 1}},
+      {"A f16 MN sw128, B bf16 MN sw64",   {32, 128, 1, 1, 128, 64, 0, 1}},
+      {"A f16 MN sw128, B bf16 MN sw128",  {128, 128, 1, 1, 128, 128, 0, 1}},
+      {"A f16 K sw128, B bf16 K sw128",    {128, 128, 0, 0, 128, 128, 0, 1}},
   };
   int fails = 0;
   for (const Case& c : cases) {

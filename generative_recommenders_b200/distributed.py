@@ -44,52 +44,95 @@ def gather_rows(values: torch.Tensor, seq_offsets: torch.Tensor, indices: Sequen
 
 
 class LayerBucketAllReduce:
-    """Averages gradients across ranks, one flat bucket per layer, overlapped with the backward of earlier layers."""
+    """Averages gradients across ranks, one flat bucket per layer, overlapped with the backward of earlier layers.
+
+    The gradients of a layer LIVE in one flat buffer of the parameters' dtype (`p.grad` is a view into it, as with DDP's
+    `gradient_as_bucket_view`), so the collective runs in place on that buffer: no concatenation, no fp32 staging copy, no
+    scatter back.  A post-accumulate-grad hook counts the parameters of a layer; when the last one has its gradient the
+    layer's slice is all-reduced (AVG on NCCL, SUM + divide on gloo) on a side stream.  `wait()` reduces whatever has not been
+    reduced in this iteration (layers with frozen or unused parameters: their slots hold zeros on every rank) and resets the
+    bookkeeping, so a partial backward can never leave ranks out of step.  Use `zero_grad()` of this object instead of the
+    optimizer's: it clears the flat buffer with one memset and keeps the views attached.
+    """
 
     def __init__(self, layers: Sequence[torch.nn.Module], world_size: int, device: torch.device):
         self.world = world_size
         self.device = device
-        self.pending: List[torch.Tensor] = []
         self.stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
         self.launched = 0
+        self._layers = []
+        by_dtype = {}
         for layer in layers:
             params = [p for p in layer.parameters() if p.requires_grad]
-            state = {"left": len(params)}
-            for p in params:
-                p.register_post_accumulate_grad_hook(self._make_hook(params, state))
+            if not params:
+                continue
+            dt = params[0].dtype
+            if any(p.dtype != dt for p in params):
+                raise RuntimeError("LayerBucketAllReduce: the parameters of one layer must share a dtype")
+            by_dtype.setdefault(dt, []).append(params)
+        self._flats = []
+        for dt, groups in by_dtype.items():
+            # every layer slice starts at a multiple of 128 elements (>= 256 B): aligned collectives, vectorised optimizer
+            sizes = [(sum(p.numel() for p in g) + 127) // 128 * 128 for g in groups]
+            flat = torch.zeros(sum(sizes), dtype=dt, device=device)
+            self._flats.append(flat)
+            lo = 0
+            for g, sz in zip(groups, sizes):
+                state = {"params": g, "slice": flat[lo:lo + sz], "seen": 0, "done": False, "views": []}
+                o = lo
+                for p in g:
+                    view = flat[o:o + p.numel()].view_as(p)
+                    state["views"].append(view)
+                    p.grad = view
+                    o += p.numel()
+                    p.register_post_accumulate_grad_hook(self._make_hook(state))
+                self._layers.append(state)
+                lo += sz
+        backend = dist.get_backend() if (world_size > 1 and dist.is_initialized()) else None
+        self._avg = backend == "nccl"
 
-    def _make_hook(self, params, state):
+    def _make_hook(self, state):
         def hook(_p):
-            state["left"] -= 1
-            if state["left"] == 0:
-                state["left"] = len(params)
-                self._reduce(params)
+            state["seen"] += 1
+            if state["seen"] == len(state["params"]) and not state["done"]:
+                self._reduce(state)
         return hook
 
-    def _reduce(self, params) -> None:
+    def _reduce(self, state) -> None:
+        state["done"] = True
+        if self.world <= 1:
+            return
         self.launched += 1
         if self.stream is not None:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(ready)
-                self._reduce_now(params)
+                self._reduce_now(state["slice"])
         else:
-            self._reduce_now(params)
+            self._reduce_now(state["slice"])
 
-    def _reduce_now(self, params) -> None:
-        flat = torch.cat([p.grad.reshape(-1) for p in params]).float()
-        dist.all_reduce(flat)
-        flat.div_(self.world)
-        o = 0
-        for p in params:
-            n = p.numel()
-            p.grad.copy_(flat[o:o + n].view_as(p.grad))
-            o += n
-        self.pending.append(flat)  # keep alive until the consumer stream has waited
+    def _reduce_now(self, flat: torch.Tensor) -> None:
+        if self._avg:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(flat)
+            flat.div_(self.world)
+
+    def zero_grad(self) -> None:
+        for flat in self._flats:
+            flat.zero_()
+        for state in self._layers:
+            for p, view in zip(state["params"], state["views"]):
+                if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                    p.grad = view  # re-attach (e.g. after an optimizer.zero_grad(set_to_none=True))
 
     def wait(self) -> None:
         """Call after backward, before the optimizer step."""
+        for state in self._layers:
+            if not state["done"]:
+                self._reduce(state)  # frozen / unused parameters: reduce what is there so that ranks stay in step
         if self.stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
-        self.pending.clear()
+        for state in self._layers:
+            state["seen"], state["done"] = 0, False

@@ -83,6 +83,20 @@ class SequentialTransductionUnitJagged(HammerModule):
         self.register_buffer("_ones_attn", torch.ones(linear_hidden_dim * num_heads), persistent=False)
         self.register_buffer("_zeros_attn", torch.zeros(linear_hidden_dim * num_heads), persistent=False)
 
+    def _check_mask(self, invalid_attn_mask: torch.Tensor, n: int) -> None:
+        """The kernel applies the causal mask the reference builds (hstu.py:626-638,704: 1 - triu(ones(n, n), 1) = tril, 1 = may
+        attend) and never reads this tensor; anything else would be silently ignored, so it is rejected.  Checked once per mask
+        tensor (one device sync)."""
+        key = (invalid_attn_mask.data_ptr(), invalid_attn_mask._version, tuple(invalid_attn_mask.shape))
+        if getattr(self, "_mask_ok", None) == key:
+            return
+        if invalid_attn_mask.dim() < 2 or invalid_attn_mask.size(-2) != n:
+            raise RuntimeError(f"invalid_attn_mask must be [..., n, n], got {tuple(invalid_attn_mask.shape)}")
+        causal = torch.tril(torch.ones(n, n, device=invalid_attn_mask.device, dtype=torch.float32))
+        if not bool((invalid_attn_mask.float() == causal).all()):
+            raise NotImplementedError("only the causal invalid_attn_mask of the reference (tril(ones)) is supported by the CUDA attention")
+        self._mask_ok = key
+
     def forward(
         self,
         x: torch.Tensor,
@@ -102,6 +116,10 @@ class SequentialTransductionUnitJagged(HammerModule):
         if kern != HammerKernel.CUDA:
             raise RuntimeError(f"generative_recommenders_b200 only implements HammerKernel.CUDA (got {kern})")
         n = invalid_attn_mask.size(-1)
+        self._check_mask(invalid_attn_mask, n)
+        if n != self._rel_attn_bias._max_seq_len:
+            raise RuntimeError(f"invalid_attn_mask is {n} x {n} but the relative bias module was built for max_seq_len "
+                               f"{self._rel_attn_bias._max_seq_len}")
         H, dqk, dv = self._num_heads, self._attention_dim, self._linear_dim
         L = x.shape[0]
         normed_x = layer_norm(x, self._ones_in, self._zeros_in, self._eps, kernel=kern)

@@ -115,8 +115,10 @@ def cuda_hstu_attention_bwd(
     keep = _fill_bias(p, bias, dbias)
     ws = _workspace(p, True, dev)
     with torch.cuda.device(dev), _lib.timed("attn_bwd", dev):
+        impl_used = _lib.lib().hstu_attn_select_impl(C.byref(p), 1)
         _lib.check(_lib.lib().hstu_attn_bwd(C.byref(p), _lib.stream_ptr(dev)), "hstu_attn_bwd")
-    _lib.note_launch(2)
+    # tcgen05 path: max|dO| pre-pass + main kernel + dQ convert; generic path: dK/dV kernel + dQ kernel
+    _lib.note_launch(3 if impl_used == _lib.IMPL_UMMA else 2)
     del ws, keep
 
 
@@ -125,6 +127,17 @@ def _fill_bias(p, bias, dbias):
         return None
     pos_w, ts_w, timestamps = bias
     keep = []
+    n, B = int(p.max_seq_len), int(p.batch)
+    # the kernels index pos_w[n - 1 + j - i] and timestamps[b * n + i] without bounds checks: the shapes are the contract
+    if pos_w is not None and pos_w.numel() != 2 * n - 1:
+        raise RuntimeError(f"relative position bias: pos_w must have 2 * max_seq_len - 1 = {2 * n - 1} entries, got {pos_w.numel()}")
+    if (ts_w is None) != (timestamps is None):
+        raise RuntimeError("relative time bias: ts_w and timestamps must be given together")
+    if ts_w is not None:
+        if tuple(timestamps.shape) != (B, n):
+            raise RuntimeError(f"relative time bias: timestamps must be [B, max_seq_len] = [{B}, {n}], got {tuple(timestamps.shape)}")
+        if ts_w.numel() < 2:
+            raise RuntimeError("relative time bias: ts_w must have num_buckets + 1 >= 2 entries")
     if pos_w is not None:
         pos_w = pos_w.detach().float().contiguous()
         p.pos_w = pos_w.data_ptr()

@@ -116,6 +116,17 @@ def cuda_norm_mul_dropout_bwd(dy, attn, u, w, b, mean, rstd, p, seed, silu_u, co
     return dattn, du, dw, db
 
 
+def _next_dropout_seed(dev: torch.device, numel: int) -> int:
+    """Seed of the counter-based dropout generator, drawn from the CUDA generator of `dev` the way torch's own dropout consumes
+    it: (initial seed, philox offset) identify the call and the offset advances by the number of random words used.  So
+    `torch.cuda.manual_seed(s)` makes the masks reproducible, ranks seeded differently get different masks, and the CPU RNG
+    stream of the caller is left alone."""
+    gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+    off = gen.get_offset()
+    gen.set_offset(off + ((numel + 3) // 4 + 3) // 4 * 4)
+    return (gen.initial_seed() * 0x9E3779B97F4A7C15 + off * 0xD1B54A32D192ED03 + 0x2545F4914F6CDD1D) & (2**64 - 1)
+
+
 def _row_major(t: torch.Tensor) -> torch.Tensor:
     return t if t.stride(-1) == 1 else t.contiguous()
 
@@ -128,7 +139,7 @@ class _HSTUComputeOutputFunction(torch.autograd.Function):
         w = norm_weight.to(attn.dtype).contiguous()
         b = norm_bias.to(attn.dtype).contiguous()
         p = float(dropout_ratio) if training else 0.0
-        seed = int(torch.randint(0, 2**62, (1,)).item()) if p > 0.0 else 0
+        seed = _next_dropout_seed(attn.device, attn.numel() * (3 if concat_ux else 1)) if p > 0.0 else 0
         y, mean, rstd = cuda_norm_mul_dropout_fwd(attn, u, w, b, eps, p, seed, silu_u, concat_ux, group_norm, num_heads,
                                                   linear_dim)
         out = torch.addmm(x, y, output_weight.to(x.dtype))

@@ -500,6 +500,27 @@ def stu_layer_fwd_bwd_timed(x, x_offsets, max_seq_len, num_targets, params, num_
     return y.detach(), x.grad
 
 
+def stu_stack_fwd_bwd(x, x_offsets, max_seq_len, num_targets, layer_params, num_heads, attn_dim, hidden_dim, dout):
+    """A whole STU stack (modules/stu.py:421-466: layers applied in sequence; each layer = stu.py:291-352, dropout 0,
+    LayerNorm output norm, concat_ux) forward + backward in fp32 on CPU with the attention through OracleAttention.
+    `layer_params`: one dict of reference parameter names per layer.  Returns (y, dx, [dict of parameter grads per layer])."""
+    h = x.detach().float().requires_grad_()
+    x_leaf = h
+    alpha = 1.0 / math.sqrt(attn_dim)
+    leaves = []
+    for params in layer_params:
+        ps = {k: v.detach().float().requires_grad_() for k, v in params.items()}
+        leaves.append(ps)
+        u, q, k, v = hstu_compute_uqvk_fwd(h, ps["_input_norm_weight"], ps["_input_norm_bias"], 1e-6, num_heads, attn_dim,
+                                           hidden_dim, ps["_uvqk_weight"], ps["_uvqk_beta"])
+        attn = OracleAttention.apply(max_seq_len, alpha, q, k, v, x_offsets, num_targets, 0, 0)
+        h = hstu_compute_output_fwd(attn.reshape(-1, num_heads * hidden_dim), u, h, ps["_output_norm_weight"],
+                                    ps["_output_norm_bias"], ps["_output_weight"], 1e-6, False, True, False, num_heads,
+                                    hidden_dim)
+    h.backward(dout.float())
+    return h.detach(), x_leaf.grad, [{k: v.grad for k, v in ps.items()} for ps in leaves]
+
+
 # --------------------------------------------------------------------------------------
 # error metric shared by the parity tests
 # --------------------------------------------------------------------------------------

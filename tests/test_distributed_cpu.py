@@ -89,3 +89,44 @@ def test_layer_bucket_allreduce_gloo_world2():
     assert out["same"], "ranks disagree after the all-reduce"
     assert out["launched"] == 3, "one bucket per layer"
     torch.testing.assert_close(out["grads"], _single_reference(), rtol=1e-5, atol=1e-6)
+
+
+def _worker_partial(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    layers = torch.nn.ModuleList([torch.nn.Linear(8, 8) for _ in range(3)])
+    red = LayerBucketAllReduce(list(layers), world, torch.device("cpu"))
+    layers[1].bias.requires_grad_(False)  # frozen after construction: its hook never fires
+    ok = True
+    for it in range(2):
+        red.zero_grad()
+        torch.manual_seed(100 + rank + 10 * it)
+        h = torch.randn(4 + rank, 8)
+        for i, l in enumerate(layers):
+            if it == 0 and i == 2:
+                continue  # iteration 0 does not use the last layer at all
+            h = torch.tanh(l(h))
+        h.square().sum().backward()
+        red.wait()
+        grads = torch.cat([p.grad.reshape(-1) for p in layers.parameters() if p.grad is not None])
+        gathered = [torch.zeros_like(grads) for _ in range(world)]
+        dist.all_gather(gathered, grads)
+        ok = ok and all(torch.equal(g, gathered[0]) for g in gathered)
+        # p.grad stays a view of the flat bucket across iterations
+        ok = ok and all(p.grad.data_ptr() == v.data_ptr() for st in red._layers for p, v in zip(st["params"], st["views"]))
+    if rank == 0:
+        out["ok"] = ok
+        out["launched"] = red.launched
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_allreduce_survives_frozen_and_unused_parameters():
+    """A layer whose hook count never completes (frozen parameter, unused branch) is reduced in wait(); counters reset."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_partial, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out["ok"], "ranks diverged or the gradient views were lost"
+    assert out["launched"] == 6, "every layer is reduced exactly once per iteration"

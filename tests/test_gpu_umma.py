@@ -51,7 +51,7 @@ def test_umma_matches_generic_at_full_size(d, lmax, B, H):
     o_ref = hstu_mha(lmax, alpha, q.float(), k.float(), v.float(), off, num_targets=nt, kernel=HammerKernel.CUDA,
                      impl=_lib.IMPL_GENERIC)
     o = hstu_mha(lmax, alpha, q, k, v, off, num_targets=nt, kernel=HammerKernel.CUDA, impl=_lib.IMPL_UMMA)
-    assert_rel(o, o_ref, f"umma vs generic d={d} lmax={lmax}", operand_roundings=1)
+    assert_rel(o, o_ref, f"umma vs generic d={d} lmax={lmax}")
     # backward: tcgen05 (where supported) vs the CUDA-core kernels on the same bf16 inputs
     do = torch.randn_like(o)
     grads = {}
@@ -60,8 +60,8 @@ def test_umma_matches_generic_at_full_size(d, lmax, B, H):
         hstu_mha(lmax, alpha, qq, kk, vv, off, num_targets=nt, kernel=HammerKernel.CUDA, impl=impl).backward(do)
         grads[impl] = (qq.grad, kk.grad, vv.grad)
     for name, a, r in zip(("dq", "dk", "dv"), grads[_lib.IMPL_AUTO], grads[_lib.IMPL_GENERIC]):
-        # both sides are bf16 (1.7e-3 storage rounding each) and the tcgen05 side rounds P / dS to bf16 once more
-        assert_rel(a, r.float(), f"bwd umma vs generic {name} d={d} lmax={lmax}", tol=3.5e-3)
+        # both sides are bf16: the reference side of this self-comparison carries its own 1.7e-3 storage rounding
+        assert_rel(a, r.float(), f"bwd umma vs generic {name} d={d} lmax={lmax}", tol=2.0e-3)
 
 
 def test_linearity_in_v_and_sequence_permutation():

@@ -54,3 +54,29 @@ def test_no_cpu_fallback():
         blk(x, off, None, torch.tril(torch.ones(24, 24)))
     with pytest.raises(NotImplementedError):
         blk(x, off, None, torch.tril(torch.ones(24, 24)), delta_x_offsets=(off, off), cache=(None,) * 4)
+
+
+def test_non_causal_mask_and_wrong_sizes_are_rejected():
+    """The kernel applies the reference's causal mask and never reads `invalid_attn_mask`: anything else must not be silently
+    ignored; a mask whose size disagrees with the bias module would index pos_w / timestamps out of bounds."""
+    blk = _mk()
+    x = torch.randn(10, 32)
+    off = torch.tensor([0, 4, 10])
+    with pytest.raises(NotImplementedError):
+        blk(x, off, None, torch.ones(24, 24))                      # full (non-causal) mask
+    with pytest.raises(RuntimeError):
+        blk(x, off, None, torch.tril(torch.ones(20, 20)))          # n != the bias module's max_seq_len
+
+
+def test_bias_shape_contract():
+    from generative_recommenders_b200 import _lib
+    from generative_recommenders_b200.ops.hstu_attention import _fill_bias
+
+    p = _lib.AttnParams()
+    p.max_seq_len, p.batch = 24, 2
+    with pytest.raises(RuntimeError):
+        _fill_bias(p, (torch.zeros(40), None, None), None)                              # pos_w must be 2n-1 = 47
+    with pytest.raises(RuntimeError):
+        _fill_bias(p, (torch.zeros(47), torch.zeros(129), torch.zeros(2, 23, dtype=torch.int64)), None)  # timestamps [B, n]
+    with pytest.raises(RuntimeError):
+        _fill_bias(p, (torch.zeros(47), torch.zeros(129), None), None)
