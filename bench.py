@@ -10,6 +10,9 @@ Workload `hstu_large` (default; BASELINE.json metric "user-seqs/sec HSTU-large L
   layer, overlapped with the remaining backward) + fused AdamW step.  value = sequences / second over all ranks.
 Workload `attn`: the reference microbench (B=512, H=4, d in {64,128}, fwd+bwd of hstu_mha only).
 
+`--impl triton` (workload attn only) times the reference's own Triton kernel (`triton_hstu_mha`, sort_by_length=True,
+enable_tma=False, autotuned; fetched into the git-ignored baseline/_ref/ by scripts/fetch_triton_baseline.py) on the same
+seeded inputs with the same CUDA-event method: the GPU comparator the north-star names.
 `--impl reference` times the CPU port of the reference eager path (oracle/) on the host cores on a bounded sample of
 the same workload (the Python reference itself cannot travel to the GPU box).  Rank 0 only.
 """
@@ -33,7 +36,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "triton"])
     ap.add_argument("--workload", default="hstu_large", choices=["hstu_large", "attn"])
     ap.add_argument("--batch", type=int, default=16, help="user sequences per GPU per step")
     ap.add_argument("--lmax", type=int, default=8192)
@@ -126,6 +129,14 @@ def synth_lengths(batch, lmax, device, seed):
     off = torch.zeros(batch + 1, dtype=torch.int64, device=device)
     off[1:] = torch.cumsum(lengths, 0)
     return lengths, nt, off
+
+
+def attn_inputs(L, heads, d, dev):
+    """q|k|v as views of one [L, H, 3d] buffer, uniform(-0.01, 0.01), dO ~ N(0,1): hstu_attention_bench.py:222-248."""
+    torch.manual_seed(2002)
+    x = torch.empty(L, heads, 3 * d, device=dev, dtype=torch.bfloat16).uniform_(-0.01, 0.01)
+    do = torch.randn(L, heads, d, device=dev, dtype=torch.bfloat16)
+    return x, do
 
 
 def attn_flops(lengths, heads, dqk, dv):
@@ -224,11 +235,10 @@ def run_ours(args):
     else:
         d = args.attn_dim
         Ha = args.attn_heads
-        x = torch.empty(L, Ha, 3 * d, device=dev, dtype=torch.bfloat16).uniform_(-0.01, 0.01)
+        x, do = attn_inputs(L, Ha, d, dev)
         q, k, v = torch.split(x, [d, d, d], dim=-1)
         q.requires_grad_(True), k.requires_grad_(True), v.requires_grad_(True)
         alpha = 1.0 / d
-        do = torch.randn(L, Ha, d, device=dev, dtype=torch.bfloat16)
         x_host = x.detach().cpu().pin_memory()
         h2d_bytes = x_host.numel() * 2
 
@@ -332,6 +342,92 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU comparator: the reference's own Triton kernel (unmodified, from baseline/_ref) on the same inputs
+# ----------------------------------------------------------------------------------------------------------------
+def run_triton(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if args.workload != "attn" or not os.path.isdir(os.path.join(ref_root, "generative_recommenders")):
+        print(json.dumps({"impl": "triton", "unavailable": "needs --workload attn and baseline/_ref (scripts/fetch_triton_baseline.py)"}))
+        return
+    sys.path.insert(0, ref_root)
+    try:
+        from generative_recommenders.ops.triton.triton_hstu_attention import triton_hstu_mha
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps({"impl": "triton", "unavailable": f"import failed: {type(e).__name__}: {e}"[:300]}))
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    lengths, nt, off = synth_lengths(args.batch, args.lmax, dev, 1001)
+    L = int(off[-1])
+    d, Ha = args.attn_dim, args.attn_heads
+    x, do = attn_inputs(L, Ha, d, dev)
+    q, k, v = torch.split(x, [d, d, d], dim=-1)
+    q.requires_grad_(True), k.requires_grad_(True), v.requires_grad_(True)
+    alpha = 1.0 / d
+    t_f, t_b = [], []
+
+    def step(record):
+        q.grad = k.grad = v.grad = None
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        o = triton_hstu_mha(args.lmax, alpha, q, k, v, off, num_targets=nt, max_attn_len=0, contextual_seq_len=0,
+                            sort_by_length=True, enable_tma=False)
+        e[1].record()
+        o.backward(do)
+        e[2].record()
+        if record:
+            t_f.append((e[0], e[1]))
+            t_b.append((e[1], e[2]))
+
+    t0 = time.perf_counter()
+    try:
+        for _ in range(max(1, args.warmup)):  # the first call autotunes (29 forward + 20 backward configurations)
+            step(False)
+        torch.cuda.synchronize()
+        tune_s = time.perf_counter() - t0
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            step(True)
+        s1.record()
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps({"impl": "triton", "unavailable": f"run failed: {type(e).__name__}: {e}"[:400],
+                          "config": {"attn_shape": {"batch": args.batch, "lmax": args.lmax, "heads": Ha, "d": d}}}))
+        return
+    ms = s0.elapsed_time(s1) / args.steps
+    ms_f = sum(a.elapsed_time(b) for a, b in t_f) / len(t_f)
+    ms_b = sum(a.elapsed_time(b) for a, b in t_b) / len(t_b)
+    fl, by = attn_flops(lengths, Ha, d, d), attn_bytes(lengths, Ha, d, d)
+    best = {}
+    try:
+        import generative_recommenders.ops.triton.triton_hstu_attention as T
+
+        for name in ("_hstu_attn_fwd", "_hstu_attn_bwd"):
+            cache = getattr(getattr(T, name), "cache", {})
+            best[name] = [str(c) for c in cache.values()][:2]
+    except Exception:  # noqa: BLE001
+        pass
+    import triton
+
+    print(json.dumps({
+        "impl": "triton", "metric": "user-seqs/sec hstu_mha fwd+bwd microbench", "value": args.batch / (ms * 1e-3),
+        "unit": "sequences/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"reference triton_hstu_mha fwd+bwd (sort_by_length=True, enable_tma=False, autotuned, triton "
+                               f"{triton.__version__}): B={args.batch}, H={Ha}, d={d}, Lmax={args.lmax}, bf16, alpha=1/d",
+                   "attn_shape": {"batch": args.batch, "lmax": args.lmax, "heads": Ha, "d": d}, "rows_per_gpu": L},
+        "kernel_ms_per_call": {"attn_fwd": round(ms_f, 4), "attn_bwd": round(ms_b, 4)},
+        "tflops": {"fwd": fl["fwd"] / (ms_f * 1e-3) / 1e12, "bwd": fl["bwd"] / (ms_b * 1e-3) / 1e12},
+        "hbm_gbs_algorithmic": {"fwd": by["fwd"] / (ms_f * 1e-3) / 1e9, "bwd": by["bwd"] / (ms_b * 1e-3) / 1e9},
+        "autotune_seconds": round(tune_s, 1), "autotune_best": best,
+    }))
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -452,5 +548,7 @@ if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "triton":
+        run_triton(a)
     else:
         run_ours(a)
