@@ -398,7 +398,12 @@ def run_triton(args):
         s1.record()
         torch.cuda.synchronize()
     except Exception as e:  # noqa: BLE001
-        print(json.dumps({"impl": "triton", "unavailable": f"run failed: {type(e).__name__}: {e}"[:400],
+        import traceback
+
+        traceback.print_exc()
+        cause = e.__cause__ or e.__context__
+        print(json.dumps({"impl": "triton", "unavailable": (f"run failed: {type(e).__name__}: {str(e)[-1500:]}"
+                                                            + (f" | cause: {type(cause).__name__}: {str(cause)[-800:]}" if cause else "")),
                           "config": {"attn_shape": {"batch": args.batch, "lmax": args.lmax, "heads": Ha, "d": d}}}))
         return
     ms = s0.elapsed_time(s1) / args.steps

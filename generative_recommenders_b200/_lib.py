@@ -66,6 +66,8 @@ _PROTOS = {
     "hstu_silu_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _i32, _vp]),
     "hstu_jagged_concat": (C.c_int, [_vp] * 5 + [_i32] * 8 + [_vp]),
     "hstu_jagged_split": (C.c_int, [_vp] * 5 + [_i32] * 8 + [_vp]),
+    "hstu_position_embeddings_fwd": (C.c_int, [_vp] * 10 + [_i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "hstu_position_embeddings_bwd": (C.c_int, [_vp] * 6 + [_i64, _i32, _f32, _i32, _vp]),
     "hstu_umma_selftest": (C.c_int, [C.c_char_p, C.c_size_t]),
 }
 

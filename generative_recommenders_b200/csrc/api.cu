@@ -239,6 +239,43 @@ int hstu_jagged_split(const void* in, void* left, void* right, const void* offse
                              dense_len_left, dense_len_right, n_prefix, D, elem_bytes, max_seq_len, (cudaStream_t)stream);
 }
 
+int hstu_position_embeddings_fwd(const void* seq_embeddings, void* out, const float* pos_w, const float* ts_w,
+                                 const void* seq_offsets, const void* seq_lengths, const void* num_targets,
+                                 const int64_t* timestamps, int32_t* pos_inds, int32_t* ts_inds, int64_t total_rows,
+                                 int32_t batch, int32_t D, int32_t max_pos_ind, int32_t num_time_buckets,
+                                 int32_t max_contextual_seq_len, float alpha, int32_t interleave_targets,
+                                 int32_t log_time_bucket, int32_t offsets_are_i64, int32_t lengths_are_i64,
+                                 int32_t num_targets_are_i64, int32_t dtype, void* stream) {
+  HSTU_CHECK_ARG(total_rows >= 0 && batch >= 0 && D > 0, "position_embeddings_fwd: bad sizes");
+  if (total_rows == 0) return 0;
+  if (int e = bind_device(seq_embeddings)) return e;
+  HSTU_CHECK_ARG(seq_embeddings && out && pos_w && ts_w && seq_offsets && seq_lengths && timestamps,
+                 "position_embeddings_fwd: NULL argument");
+  HSTU_CHECK_ARG(max_pos_ind > 0 && num_time_buckets >= 0, "position_embeddings_fwd: empty embedding table");
+  PosArgs a;
+  a.seq = seq_embeddings; a.out = out; a.pos_w = pos_w; a.ts_w = ts_w;
+  a.seq_offsets = seq_offsets; a.seq_lengths = seq_lengths; a.num_targets = num_targets;
+  a.timestamps = reinterpret_cast<const long long*>(timestamps);
+  a.pos_inds = pos_inds; a.ts_inds = ts_inds;
+  a.L = total_rows; a.B = batch; a.D = D;
+  a.max_pos_ind = max_pos_ind; a.num_time_buckets = num_time_buckets; a.max_contextual = max_contextual_seq_len;
+  a.offsets_i64 = offsets_are_i64; a.lengths_i64 = lengths_are_i64; a.targets_i64 = num_targets_are_i64;
+  a.interleave = interleave_targets; a.log_bucket = log_time_bucket;
+  a.vec_ok = (((uintptr_t)seq_embeddings | (uintptr_t)out | (uintptr_t)pos_w | (uintptr_t)ts_w) & 15) == 0;
+  a.alpha = alpha;
+  return position_fwd(a, dtype, (cudaStream_t)stream);
+}
+
+int hstu_position_embeddings_bwd(const void* dout, void* d_seq_embeddings, float* d_pos_w, float* d_ts_w,
+                                 const int32_t* pos_inds, const int32_t* ts_inds, int64_t total_rows, int32_t D, float alpha,
+                                 int32_t dtype, void* stream) {
+  HSTU_CHECK_ARG(total_rows >= 0 && D > 0, "position_embeddings_bwd: bad sizes");
+  if (total_rows == 0) return 0;
+  if (int e = bind_device(dout)) return e;
+  HSTU_CHECK_ARG(dout && d_seq_embeddings && d_pos_w && d_ts_w && pos_inds && ts_inds, "position_embeddings_bwd: NULL argument");
+  return position_bwd(dout, d_seq_embeddings, d_pos_w, d_ts_w, pos_inds, ts_inds, total_rows, D, alpha, dtype, (cudaStream_t)stream);
+}
+
 int hstu_umma_selftest(char* report, size_t report_bytes) { return umma_selftest(report, report_bytes); }
 
 }  // extern "C"

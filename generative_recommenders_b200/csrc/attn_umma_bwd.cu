@@ -68,12 +68,11 @@ struct BwdCfg {
   static constexpr int OFF_DO = OFF_Q + STAGES * TILE_BYTES;
   // dS^T boxes [kv][q] (tile i -> pair buffer i & 1): read K-major as A of dK (M = kv) and MN-major as A of dQ (M = q)
   static constexpr int OFF_DST = OFF_DO + STAGES * TILE_BYTES;
-  // dQ staging (source of the TMA reduce-add): per warpgroup one box of 128 query rows x DQ_BOX_COLS fp32 columns; a
-  // warpgroup owns D/2 columns of dQ and sends them in DQ_NPASS boxes
-  static constexpr int DQ_BOX_COLS = (D / 2 < 32) ? D / 2 : 32;
-  static constexpr int DQ_NPASS = (D / 2) / DQ_BOX_COLS;
+  // dQ staging (source of the TMA reduce-add): two alternating boxes of 128 query rows x 32 fp32 columns (128B swizzle); the
+  // drain warpgroup sends the D columns of a dQ tile in DQ_NPASS boxes
+  static constexpr int DQ_BOX_COLS = 32;
+  static constexpr int DQ_NPASS = D / DQ_BOX_COLS;
   static constexpr int DQS_BYTES = 128 * DQ_BOX_COLS * 4;
-  static_assert(DQ_BOX_COLS * 4 == SW, "the staging box uses the operand swizzle width");
   static constexpr int OFF_DQS = OFF_DST + 2 * PT_BYTES;
   static constexpr int OFF_BAR = OFF_DQS + 2 * DQS_BYTES;
   static_assert(OFF_BAR + 256 + 1024 <= 232448, "shared memory budget");
@@ -166,8 +165,18 @@ __global__ void dout_amax_kernel(const uint16_t* __restrict__ dout, long long ro
   }
 }
 
+template <int NREG>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NREG)); }
+template <int NREG>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NREG)); }
+__device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// 512 threads = 4 warpgroups with their own register budgets (setmaxnreg; 128 regs / thread at launch):
+//   warps 0-3   issuers X (scores), YV (dV), YK (dK), Z (dQ): one elected lane each                      -> 64 regs
+//   warps 4-11  two elementwise warpgroups (64 scores + 64 dP per thread in flight)                       -> 176 regs
+//   warps 12-15 dQ drain warpgroup; its elected lane is also the TMA producer (both follow tile_done)     -> 88 regs
 template <int D, bool BF16>
-__global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = BwdCfg<D>;
   constexpr int SW = Cfg::SW;
   constexpr int NST = Cfg::STAGES;
@@ -210,12 +219,12 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     mbar_init(&bars->kv_full, 1);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->q_full[i], 1);
-      mbar_init(&bars->tile_done[i], 2);
+      mbar_init(&bars->tile_done[i], 3);   // the commits of YV, YK and Z
     }
     for (int i = 0; i < 3; ++i) mbar_init(&bars->s_full[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bars->unit_done[i], 128);
-    for (int i = 0; i < 2; ++i) mbar_init(&bars->dq_empty[i], 256);
-    mbar_init(&bars->fin_full, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&bars->dq_empty[i], 128);
+    mbar_init(&bars->fin_full, 2);         // YV (dV) and YK (dK)
     for (int i = 0; i < 3; ++i) mbar_init(&bars->slot_free[i], 1);
     fence_barrier_init();
   }
@@ -225,146 +234,206 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
+  if (warp < 4) {
+    reg_dealloc<64>();
+    // ---------------- MMA issuers ----------------
+    // Work is pipelined in "units" u = 2 i + h: half h (64 query rows) of query tile i.  Unit u's scores live in TMEM
+    // slot u % NSLOT; warpgroup h turns them into P^T (fp16, over the front of the slot) and the dS^T box (pair i & 1,
+    // box h) in shared memory.  FOUR threads issue, each with its own wait -> issue -> commit loop: a tcgen05.mma blocks its
+    // issuing thread until the tensor pipe accepts it and a commit costs the thread ~100-200 clk more, so the thread with the
+    // most MMAs per unit sets the pace of the CTA (r01: one thread with dV + dK = 8 MMAs + 2 commits per unit was busy 100 % of
+    // the time and the whole kernel ran at its rate; profiles/r01_bwd_timeline.txt).
+    //   X (warp 0): S^T, dP^T.   YV (warp 1): dV.   YK (warp 2): dK.   Z (warp 3): dQ of every tile.
+    // The whole warp runs the warp-uniform control flow, one fixed lane issues; descriptors are built once.
+    constexpr int NSLOT = Cfg::NSLOT;
+    const bool leader = lane == 0;
+    const int U = 2 * T;
+    if (warp == 0) {
+      constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, BF16, BF16);    // S^T, dP^T half-tiles
+      const uint64_t dk_k = desc_kmajor<SW>(smem_u32(sK), 0);                        // K as K-major A (S^T)
+      const uint64_t dv_k = desc_kmajor<SW>(smem_u32(sV), 0);                        // V as K-major A (dP^T)
+      const uint64_t dq_k = desc_kmajor<SW>(smem_u32(sQ), 0);                        // Q_i rows as K-major B
+      const uint64_t ddo_k = desc_kmajor<SW>(smem_u32(sDO), 0);                      // dO_i rows as K-major B
+      mbar_wait(&bars->kv_full, 0);
+      tc_fence_after_sync();
+      for (int u = 0; u < U; ++u) {
+        const int i = u >> 1, hf = u & 1, st = i % NST, slot = u % NSLOT;
+        if (leader) HSTU_TSTAMP(0, u, 0);
+        if (u >= NSLOT) {  // the slot still holds P^T of unit u - NSLOT until its dV GEMM has completed
+          mbar_wait(&bars->slot_free[slot], (u / NSLOT - 1) & 1);
+          tc_fence_after_sync();
+        }
+        if (hf == 0) {
+          mbar_wait(&bars->q_full[st], (i / NST) & 1);
+          tc_fence_after_sync();
+        }
+        // query rows [64 hf, 64 hf + 64) of the staged Q_i / dO_i tiles
+        const uint64_t row_off = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);
+        const uint32_t ts = tmem + Cfg::TMEM_SLOT + slot * 128;
+        if (leader) {
+          HSTU_TSTAMP(0, u, 1);
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
+            const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
+            mma_ss(ts, dk_k + o, dq_k + row_off + o, idesc_s, ks > 0);
+          }
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
+            const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
+            mma_ss(ts + 64, dv_k + o, ddo_k + row_off + o, idesc_s, ks > 0);
+          }
+          mma_commit(&bars->s_full[u % Cfg::NSF]);
+          HSTU_TSTAMP(0, u, 2);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      // ---- issuer YV: dV += P^T dO (A = P^T from the unit's TMEM slot) of every unit; its commit frees the slot ----
+      constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // A = P^T from TMEM, B MN-major
+      const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
+      for (int u = 0; u < U; ++u) {
+        const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1, slot = u % NSLOT;
+        // P^T / dS^T of the unit are written.  One barrier per (half, tile parity): with a 3-slot score ring a warpgroup may
+        // finish TWO units before this thread gets here; a single barrier per half would then be two phases ahead and the
+        // parity wait would alias.
+        if (leader) HSTU_TSTAMP(1, u, 0);
+        mbar_wait(&bars->unit_done[hf * 2 + pb], (i >> 1) & 1);
+        tc_fence_after_sync();
+        const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);  // MN-major B: K rows = the 64 query rows
+        const uint32_t tp = tmem + Cfg::TMEM_SLOT + slot * 128;
+        if (leader) {
+          HSTU_TSTAMP(1, u, 1);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
+            mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (u > 0) || (ks > 0));
+          mma_commit(&bars->slot_free[slot]);                // the score issuer may overwrite the slot
+          if (hf == 1) mma_commit(&bars->tile_done[i & 3]);  // this issuer is done with dO_i
+          HSTU_TSTAMP(1, u, 2);
+        }
+        __syncwarp();
+      }
+      if (leader) mma_commit(&bars->fin_full);
+      __syncwarp();
+    } else if (warp == 2) {
+      // ---- issuer YK: dK += dS^T Q (A = the unit's dS^T box in shared memory) of every unit ----
+      constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // A = dS^T K-major, B MN-major
+      const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box [kv][q] as K-major A
+      const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
+      for (int u = 0; u < U; ++u) {
+        const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1;
+        if (leader) HSTU_TSTAMP(4, u, 0);
+        mbar_wait(&bars->unit_done[hf * 2 + pb], (i >> 1) & 1);
+        tc_fence_after_sync();
+        const uint64_t box = (uint64_t)((pb * Cfg::PT_BYTES + hf * 16384) >> 4);
+        const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);
+        if (leader) {
+          HSTU_TSTAMP(4, u, 1);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_ss(tmem + Cfg::TMEM_DK, dds_k + box + (uint64_t)((ks * 32) >> 4), dq_mn + rows + (uint64_t)((ks * 16 * SW) >> 4),
+                   idesc_kv, (u > 0) || (ks > 0));
+          if (hf == 1) mma_commit(&bars->tile_done[i & 3]);  // this issuer is done with Q_i and (as A of dK) the dS^T boxes of tile i
+          HSTU_TSTAMP(4, u, 2);
+        }
+        __syncwarp();
+      }
+      if (leader) mma_commit(&bars->fin_full);
+      __syncwarp();
+    } else {
+      // ---- issuer Z: dQ_i = dS_i K (A = the dS^T box pair read MN-major, M = 128 query rows) of every query tile ----
+      constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // A = dS^T MN-major, B MN-major
+      const uint64_t dds_mn = desc_mnmajor<128>(smem_u32(sDST), 0, 16384);           // the box pair as MN-major A
+      const uint64_t dk_mn = desc_mnmajor<SW>(smem_u32(sK), 0, Cfg::BOX_BYTES);      // K as MN-major B
+      mbar_wait(&bars->kv_full, 0);
+      for (int i = 0; i < T; ++i) {
+        const int pb = i & 1;
+        mbar_wait(&bars->unit_done[0 * 2 + pb], (i >> 1) & 1);
+        mbar_wait(&bars->unit_done[1 * 2 + pb], (i >> 1) & 1);
+        if (i >= Cfg::NDQ) mbar_wait(&bars->dq_empty[i % Cfg::NDQ], ((i / Cfg::NDQ) - 1) & 1);  // dQ_{i-NDQ} has been drained from this accumulator
+        tc_fence_after_sync();
+        if (leader) {
+          const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);  // the dS^T boxes of this query tile
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows, 16 per step
+            mma_ss(tmem + Cfg::TMEM_DQ + (i % Cfg::NDQ) * D, dds_mn + pair + (uint64_t)((ks * 16 * 128) >> 4),
+                   dk_mn + (uint64_t)((ks * 16 * SW) >> 4), idesc_dq, ks > 0);
+          mma_commit(&bars->tile_done[i & 3]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 12) {
+    reg_dealloc<88>();
+    // ---------------- dQ drain warpgroup (+ TMA producer on its elected lane) ----------------
+    // dQ tile of query tile i: TMEM (lane = query row) -> swizzled fp32 staging box (32 columns) in shared memory -> ONE TMA
+    // reduce-add per box into dq_acc.  Two staging boxes alternate, so a reduce may still be reading one while the next is being
+    // filled.  (r01 had the elementwise warpgroups drain dQ themselves: ~750 clk per tile taken from the stage that is the
+    // slowest of the kernel.)  The producer duty follows the same barrier: once tile i is done, its Q / dO stage is free for
+    // tile i + NST.
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;              // query row inside the tile == TMEM lane
+    const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
+    const bool elected = warp == 12 && lane == 0;
+    auto load_tile = [&](int i) {
+      const int st = i % NST;
+      mbar_arrive_expect_tx(&bars->q_full[st], 2 * Cfg::TILE_BYTES);
+      const int qrow = (int)(row0 + (long long)q_tile(i) * 128);
+#pragma unroll
+      for (int bx = 0; bx < Cfg::NBOX; ++bx) {
+        tma_load_3d(sQ + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, &p.tmQ, &bars->q_full[st], bx * Cfg::BOX_COLS, h, qrow);
+        tma_load_3d(sDO + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, &p.tmDO, &bars->q_full[st], bx * Cfg::BOX_COLS, h, qrow);
+      }
+    };
+    if (elected) {
       prefetch_tensormap(&p.tmK);
       prefetch_tensormap(&p.tmV);
       prefetch_tensormap(&p.tmQ);
       prefetch_tensormap(&p.tmDO);
+      prefetch_tensormap(&p.tmDQ);
       mbar_arrive_expect_tx(&bars->kv_full, 2 * Cfg::TILE_BYTES);
 #pragma unroll
       for (int bx = 0; bx < Cfg::NBOX; ++bx) {
         tma_load_3d(sK + bx * Cfg::BOX_BYTES, &p.tmK, &bars->kv_full, bx * Cfg::BOX_COLS, h, (int)(row0 + n0));
         tma_load_3d(sV + bx * Cfg::BOX_BYTES, &p.tmV, &bars->kv_full, bx * Cfg::BOX_COLS, h, (int)(row0 + n0));
       }
-      for (int i = 0; i < T; ++i) {
-        const int st = i % NST;
-        if (i >= NST) mbar_wait(&bars->tile_done[(i - NST) & 3], ((i - NST) >> 2) & 1);  // tile i - NST is done with this stage
-        mbar_arrive_expect_tx(&bars->q_full[st], 2 * Cfg::TILE_BYTES);
-        const int qrow = (int)(row0 + (long long)q_tile(i) * 128);
-#pragma unroll
-        for (int bx = 0; bx < Cfg::NBOX; ++bx) {
-          tma_load_3d(sQ + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, &p.tmQ, &bars->q_full[st], bx * Cfg::BOX_COLS, h, qrow);
-          tma_load_3d(sDO + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, &p.tmDO, &bars->q_full[st], bx * Cfg::BOX_COLS, h, qrow);
-        }
-      }
+      for (int i = 0; i < NST && i < T; ++i) load_tile(i);
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuers: warps 1, 2, 3 ----------------
-    // Work is pipelined in "units" u = 2 i + h: half h (64 query rows) of query tile i.  Unit u's scores live in TMEM
-    // slot u % NSLOT; warpgroup h turns them into P^T (bf16, over the front of the slot) and the dS^T box (pair i & 1,
-    // box h) in shared memory.  Three threads issue, each with its own wait -> issue -> commit loop: measured
-    // (umma_selftest mma-multi), one thread that commits after 8 MMAs reaches 71-84 clk / MMA, two threads 41-47, three 40,
-    // because tcgen05.commit and the barrier waits stall only their own issuer.
-    //   X (this warp): S^T, dP^T of every unit.     Y (warp 2): dV, dK of every unit.     Z (warp 3): dQ of every tile.
-    // The whole warp runs the warp-uniform control flow, one fixed lane issues; descriptors are built once.
-    constexpr int NSLOT = Cfg::NSLOT;
-    const bool leader = lane == 0;
-    constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, BF16, BF16);    // S^T, dP^T half-tiles
-    const uint64_t dk_k = desc_kmajor<SW>(smem_u32(sK), 0);                        // K as K-major A (S^T)
-    const uint64_t dv_k = desc_kmajor<SW>(smem_u32(sV), 0);                        // V as K-major A (dP^T)
-    const uint64_t dq_k = desc_kmajor<SW>(smem_u32(sQ), 0);                        // Q_i rows as K-major B
-    const uint64_t ddo_k = desc_kmajor<SW>(smem_u32(sDO), 0);                      // dO_i rows as K-major B
-    const int U = 2 * T;
-    mbar_wait(&bars->kv_full, 0);
-    tc_fence_after_sync();
-    for (int u = 0; u < U; ++u) {
-      const int i = u >> 1, hf = u & 1, st = i % NST, slot = u % NSLOT;
-      if (leader) HSTU_TSTAMP(0, u, 0);
-      if (u >= NSLOT) {  // the slot still holds P^T of unit u - NSLOT until its dV GEMM has completed
-        mbar_wait(&bars->slot_free[slot], (u / NSLOT - 1) & 1);
-        tc_fence_after_sync();
-      }
-      if (hf == 0) {
-        mbar_wait(&bars->q_full[st], (i / NST) & 1);
-        tc_fence_after_sync();
-      }
-      // query rows [64 hf, 64 hf + 64) of the staged Q_i / dO_i tiles
-      const uint64_t row_off = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);
-      const uint32_t ts = tmem + Cfg::TMEM_SLOT + slot * 128;
-      if (leader) {
-        HSTU_TSTAMP(0, u, 1);
-#pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
-          const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
-          mma_ss(ts, dk_k + o, dq_k + row_off + o, idesc_s, ks > 0);
-        }
-#pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
-          const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
-          mma_ss(ts + 64, dv_k + o, ddo_k + row_off + o, idesc_s, ks > 0);
-        }
-        mma_commit(&bars->s_full[u % Cfg::NSF]);
-        HSTU_TSTAMP(0, u, 2);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 2) {
-    // ---- issuer Y: dV += P^T dO (A = P^T from the unit's TMEM slot) and dK += dS^T Q (A = the dS^T box) of every unit ----
-    constexpr int NSLOT = Cfg::NSLOT;
-    const bool leader = lane == 0;
-    constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, false, BF16);    // A (P^T / dS^T: always fp16) K-major, B MN-major
-    const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box [kv][q] as K-major A (dK)
-    const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
-    const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
-    const int U = 2 * T;
-    for (int u = 0; u < U; ++u) {
-      const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1, slot = u % NSLOT;
-      // P^T / dS^T of the unit are written.  One barrier per (half, tile parity): with a 3-slot score ring a warpgroup may
-      // finish TWO units before this thread gets here; a single barrier per half would then be two phases ahead and the
-      // parity wait would alias.
-      if (leader) HSTU_TSTAMP(1, u, 0);
-      mbar_wait(&bars->unit_done[hf * 2 + pb], (i >> 1) & 1);
-      tc_fence_after_sync();
-      if (leader) HSTU_TSTAMP(1, u, 1);
-      const uint64_t box = (uint64_t)((pb * Cfg::PT_BYTES + hf * 16384) >> 4);
-      const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);  // MN-major B: K rows = the 64 query rows
-      const uint32_t tp = tmem + Cfg::TMEM_SLOT + slot * 128;
-      if (leader) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
-          mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (u > 0) || (ks > 0));
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          mma_ss(tmem + Cfg::TMEM_DK, dds_k + box + (uint64_t)((ks * 32) >> 4), dq_mn + rows + (uint64_t)((ks * 16 * SW) >> 4),
-                 idesc_kv, (u > 0) || (ks > 0));
-        mma_commit(&bars->slot_free[slot]);                // the score issuer may overwrite the slot
-        if (hf == 1) mma_commit(&bars->tile_done[i & 3]);  // this issuer is done with Q_i / dO_i and the dS^T boxes of tile i
-        HSTU_TSTAMP(1, u, 2);
-      }
-      __syncwarp();
-    }
-    if (leader) mma_commit(&bars->fin_full);
-    __syncwarp();
-  } else if (warp == 3) {
-    // ---- issuer Z: dQ_i = dS_i K (A = the dS^T box pair read MN-major, M = 128 query rows) of every query tile ----
-    const bool leader = lane == 0;
-    constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, false, BF16);     // A (dS^T: fp16) MN-major, B MN-major
-    const uint64_t dds_mn = desc_mnmajor<128>(smem_u32(sDST), 0, 16384);           // the box pair as MN-major A
-    const uint64_t dk_mn = desc_mnmajor<SW>(smem_u32(sK), 0, Cfg::BOX_BYTES);      // K as MN-major B
+    int box = 0;  // staging box counter (box & 1 = buffer)
     for (int i = 0; i < T; ++i) {
-      const int pb = i & 1;
-      if (leader) HSTU_TSTAMP(4, i, 0);
-      mbar_wait(&bars->unit_done[0 * 2 + pb], (i >> 1) & 1);
-      mbar_wait(&bars->unit_done[1 * 2 + pb], (i >> 1) & 1);
-      if (i >= Cfg::NDQ) mbar_wait(&bars->dq_empty[i % Cfg::NDQ], ((i / Cfg::NDQ) - 1) & 1);  // dQ_{i-NDQ} has been drained from this accumulator
+      mbar_wait(&bars->tile_done[i & 3], (i >> 2) & 1);
       tc_fence_after_sync();
-      if (leader) {
-        HSTU_TSTAMP(4, i, 1);
-        const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);  // the dS^T boxes of this query tile
+      if (elected && i + NST < T) load_tile(i + NST);
+      const int qpos = q_tile(i) * 128 + row;
+      const bool q_ok = qpos < len;                // rows past the end of this sequence belong to the next one: add zeros
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows, 16 per step
-          mma_ss(tmem + Cfg::TMEM_DQ + (i % Cfg::NDQ) * D, dds_mn + pair + (uint64_t)((ks * 16 * 128) >> 4),
-                 dk_mn + (uint64_t)((ks * 16 * SW) >> 4), idesc_dq, ks > 0);
-        mma_commit(&bars->tile_done[i & 3]);
-        HSTU_TSTAMP(4, i, 2);
+      for (int ps = 0; ps < Cfg::DQ_NPASS; ++ps, ++box) {
+        const uint32_t sbox = smem_u32(sDQS + (box & 1) * Cfg::DQS_BYTES);
+        if (elected) bulk_wait_group_read1();      // the reduce that used this box (two boxes ago) has finished reading it
+        named_bar_sync(1, 128);
+        uint32_t r[32];
+        tmem_ld32(tmem + Cfg::TMEM_DQ + (i % Cfg::NDQ) * D + ps * 32 + lane_bits, r);
+        tmem_ld_wait();
+        if (ps == Cfg::DQ_NPASS - 1) {
+          tc_fence_before_sync();
+          mbar_arrive(&bars->dq_empty[i % Cfg::NDQ]);
+        }
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          st_shared_v4(sbox + swizzled_chunk_offset<128>(row, e >> 2), q_ok ? r[e] : 0u, q_ok ? r[e + 1] : 0u,
+                       q_ok ? r[e + 2] : 0u, q_ok ? r[e + 3] : 0u);
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (elected) {
+          tma_reduce_add_3d(&p.tmDQ, sbox, ps * 32, h, (int)(row0 + q_tile(i) * 128));
+          bulk_commit_group();
+        }
       }
-      __syncwarp();
     }
-  } else if (warp >= 4) {
+    if (elected) bulk_wait_group_read0();          // shared memory must stay valid until the last reduce has read it
+  } else {
+    reg_alloc<176>();
     // ---------------- elementwise warpgroups ----------------
     const int wg = (warp - 4) >> 2;                // owns query columns [64*wg, 64*wg + 64) of every tile
     const int quad = warp & 3;
@@ -381,44 +450,6 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
     const bool j_ok = j_pos < len;
     const bool j_hist = j_ok && (!msk.has_tgt || j_pos < msk.max_id);  // fast mask: valid = (j_hist & i > j) | (i == j)
     const int cbase = wg * 64;
-    const int qcol0 = wg * (D / 2);                // dQ columns drained by this warpgroup
-
-    // dQ tile of query tile i: TMEM (lane = query row) -> swizzled fp32 staging box in shared memory -> ONE TMA reduce-add
-    // per warpgroup into dq_acc.  (Per-thread red.global.add.v4 cost one L1 wavefront per lane: 1024 per tile, ~40% of the
-    // L1 data pipe that the tensor core's operand fetches also go through; measured with ncu.)
-    const uint32_t sDQSw = smem_u32(sDQS + wg * Cfg::DQS_BYTES);
-    const bool dq_issuer = quad == 0 && lane == 0;
-    auto drain_dq = [&](int i) {
-      mbar_wait(&bars->tile_done[i & 3], (i >> 2) & 1);
-      tc_fence_after_sync();
-      const int qpos = q_tile(i) * 128 + row;
-      const bool q_ok = qpos < len;                // rows past the end of this sequence belong to the next one: add zeros
-#pragma unroll
-      for (int ps = 0; ps < Cfg::DQ_NPASS; ++ps) {
-        if (dq_issuer) bulk_wait_group_read0();    // the previous reduce has finished reading the staging box
-        named_bar_sync(1 + wg, 128);
-#pragma unroll
-        for (int c = 0; c < Cfg::DQ_BOX_COLS / 16; ++c) {
-          uint32_t r[16];
-          tmem_ld16(tmem + Cfg::TMEM_DQ + (i % Cfg::NDQ) * D + qcol0 + ps * Cfg::DQ_BOX_COLS + c * 16 + lane_bits, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            st_shared_v4(sDQSw + swizzled_chunk_offset<SW>(row, c * 4 + (e >> 2)), q_ok ? r[e] : 0u, q_ok ? r[e + 1] : 0u,
-                         q_ok ? r[e + 2] : 0u, q_ok ? r[e + 3] : 0u);
-        }
-        if (ps == Cfg::DQ_NPASS - 1) {
-          tc_fence_before_sync();
-          mbar_arrive(&bars->dq_empty[i % Cfg::NDQ]);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1 + wg, 128);
-        if (dq_issuer) {
-          tma_reduce_add_3d(&p.tmDQ, sDQSw, qcol0 + ps * Cfg::DQ_BOX_COLS, h, (int)(row0 + q_tile(i) * 128));
-          bulk_commit_group();
-        }
-      }
-    };
 
     for (int i = 0; i < T; ++i) {
       const int u = 2 * i + wg, slot = u % Cfg::NSLOT;
@@ -436,15 +467,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
       const uint32_t st_addr = tmem + Cfg::TMEM_SLOT + slot * 128 + lane_bits;
       const uint32_t dp_addr = st_addr + 64;
-#ifdef HSTU_EXP_NO_ELEM
-      if (i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // keep the protocol intact
-#endif
 #pragma unroll
-#ifdef HSTU_EXP_NO_ELEM
-      for (int c = 0; c < (T < 0 ? 2 : 0); ++c) {  // ablation experiment only
-#else
       for (int c = 0; c < 2; ++c) {  // 2 chunks of 32 query columns
-#endif
         uint32_t s[32], dp[32];
         tmem_ld32(st_addr + c * 32, s);
         tmem_ld32(dp_addr + c * 32, dp);
@@ -468,8 +492,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
           for (int e = 0; e < 32; e += 2) {
             float p0, p1, d0, d1;
             HSTU_BWD_ELEM2(e, p0, p1, d0, d1);
-            pp[e >> 1] = pack_f16x2_sat(p0, p1);
-            dd[e >> 1] = pack_f16x2_sat(d0, d1);
+            pp[e >> 1] = pack_operand<BF16>(p0, p1);
+            dd[e >> 1] = pack_operand<BF16>(d0, d1);
           }
         } else if (mode == 1) {
           // valid(i, j) = ((j is history) & (i > j)) | (i == j), restricted to i < len and j < len
@@ -484,8 +508,8 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
             const bool v1 = ((c0 + 1 > lo_c) | (c0 + 1 == dg_c)) & (c0 + 1 < len_rel);
             p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;
             p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;
-            pp[e >> 1] = pack_f16x2_sat(p0, p1);
-            dd[e >> 1] = pack_f16x2_sat(d0, d1);
+            pp[e >> 1] = pack_operand<BF16>(p0, p1);
+            dd[e >> 1] = pack_operand<BF16>(d0, d1);
           }
         } else {
 #pragma unroll
@@ -497,13 +521,13 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
             const bool v1 = j_ok && i_pos + 1 < len && mask_valid(msk, i_pos + 1, j_pos);
             p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;
             p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;
-            pp[e >> 1] = pack_f16x2_sat(p0, p1);
-            dd[e >> 1] = pack_f16x2_sat(d0, d1);
+            pp[e >> 1] = pack_operand<BF16>(p0, p1);
+            dd[e >> 1] = pack_operand<BF16>(d0, d1);
           }
         }
 #undef HSTU_BWD_ELEM2
         if (c == 0 && i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
-        // P^T chunk c (32 bf16 = 16 columns) overwrites the already-read front of the S^T half of the slot: A of the dV GEMM
+        // P^T chunk c (32 fp16 = 16 columns) overwrites the already-read front of the S^T half of the slot: A of the dV GEMM
         tmem_st16(st_addr + c * 16, pp);
         // dS^T [kv][q] (16-byte stores): A of dK as stored, A of dQ read MN-major
 #pragma unroll
@@ -515,11 +539,7 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_umma_kernel(const __grid_cons
       fence_proxy_async_smem();
       if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 2);
       mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);
-      if (i >= Cfg::LAG) drain_dq(i - Cfg::LAG);  // LAG = 2: dQ_{i-2} finished long ago, no stall
-      if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 3);
     }
-    for (int t = (T > Cfg::LAG ? T - Cfg::LAG : 0); t < T; ++t) drain_dq(t);
-    if (dq_issuer) bulk_wait_group_read0();      // shared memory must stay valid until the last reduce has read it
     // ---------------- epilogue: dV (warpgroup 0) / dK (warpgroup 1): TMEM -> scale -> global ----------------
     mbar_wait(&bars->fin_full, 0);
     tc_fence_after_sync();
@@ -659,7 +679,7 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   cudaMemset(tbuf, 0, tbytes);
   cudaMemcpyToSymbol(g_trace, &tbuf, sizeof(tbuf));
 #endif
-  kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(bp);
+  kern<<<grid, 512, Cfg::SMEM_BYTES, st>>>(bp);
   HSTU_CUDA_OK(cudaGetLastError());
 #ifdef HSTU_TRACE
   {

@@ -196,9 +196,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
   } else if (warp == 2) {
     // ---------------- MMA issuer 2: O += P_i V_i (A = P from TMEM, B = V read MN-major) ----------------
     const bool leader = lane == 0;
-    // A = P is ALWAYS fp16 (11-bit significand: its rounding stays well inside the 1e-3 parity budget, a bf16 P does not);
-    // B = V keeps the input dtype.  kind::f16 takes the two operand formats independently (umma_selftest "A f16" cases).
-    constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, false, BF16);
+    constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, BF16, BF16);
     const uint64_t dv0 = desc_mnmajor<SW>(smem_u32(sV), 0, Cfg::BOX_BYTES);
     for (int i = 0; i < T; ++i) {
       const int st = i % 3;
@@ -258,7 +256,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
             const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), ah2);
             const float2 pv = __ffma2_rn(hh, make_float2(tanh_approx(hh.x), tanh_approx(hh.y)), hh);
             const float p0 = pv.x, p1 = pv.y;
-            pk[e >> 1] = pack_f16x2_sat(p0, p1);
+            pk[e >> 1] = pack_operand<BF16>(p0, p1);
           }
         } else if (mode == 1) {
 #pragma unroll
@@ -269,7 +267,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
             float p0 = pv.x, p1 = pv.y;
             p0 = ((j0 < lim_rel) | (j0 == diag_rel)) ? p0 : 0.f;
             p1 = ((j0 + 1 < lim_rel) | (j0 + 1 == diag_rel)) ? p1 : 0.f;
-            pk[e >> 1] = pack_f16x2_sat(p0, p1);
+            pk[e >> 1] = pack_operand<BF16>(p0, p1);
           }
         } else {
 #pragma unroll
@@ -280,7 +278,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
             float p0 = pv.x, p1 = pv.y;
             p0 = (j < len && mask_valid(msk, i_pos, j)) ? p0 : 0.f;
             p1 = (j + 1 < len && mask_valid(msk, i_pos, j + 1)) ? p1 : 0.f;
-            pk[e >> 1] = pack_f16x2_sat(p0, p1);
+            pk[e >> 1] = pack_operand<BF16>(p0, p1);
           }
         }
         // P chunk c (32 bf16 = 16 columns) goes to columns [16 c, 16 c + 16) of the slot: a region of S that has already

@@ -37,6 +37,29 @@ int silu_fwd_bwd(const void* x, const void* dy, void* out, long long n, int cols
                  long long os, int dtype, bool bwd, cudaStream_t st);
 int norm_partial_rows();
 
+// position.cu
+struct PosArgs {
+  const void* seq;      // [L, D] activation dtype
+  void* out;            // [L, D]
+  const float* pos_w;   // [max_pos_ind, D] fp32
+  const float* ts_w;    // [ts_rows, D] fp32
+  const void* seq_offsets;   // [B+1]
+  const void* seq_lengths;   // [B]
+  const void* num_targets;   // [B] or NULL
+  const long long* timestamps;  // [L] int64
+  int* pos_inds;        // [L] out (saved for backward) or NULL
+  int* ts_inds;         // [L] out or NULL
+  long long L;
+  int B, D;
+  int max_pos_ind, num_time_buckets, max_contextual;
+  int offsets_i64, lengths_i64, targets_i64;
+  int interleave, log_bucket, vec_ok;
+  float alpha;
+};
+int position_fwd(const PosArgs& a, int dtype, cudaStream_t st);
+int position_bwd(const void* dout, void* dseq, float* dpos, float* dts, const int* pos_inds, const int* ts_inds, long long L, int D,
+                 float alpha, int dtype, cudaStream_t st);
+
 // jagged.cu
 int jagged_concat_split(bool split, const void* a, const void* b, void* c, void* c2, const void* off_l, const void* off_r,
                         int is_i64, int batch, int dense_l, int dense_r, int n_prefix, int D, int elem_bytes,

@@ -264,6 +264,12 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// 16-bit tensor-core operand pair in the format the kernel's MMAs use (kind::f16 needs the SAME format for A and B: a mixed
+// fp16 x bf16 instruction descriptor raises "illegal instruction" on B200 -- umma_selftest reports the probe)
+template <bool OP_BF16>
+__device__ __forceinline__ uint32_t pack_operand(float lo, float hi) {
+  return OP_BF16 ? pack_bf16x2(lo, hi) : pack_f16x2_sat(lo, hi);
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
 #ifdef HSTU_EXP_NO_STS
   if (saddr != 0xffffffffu) return;  // ablation experiment only

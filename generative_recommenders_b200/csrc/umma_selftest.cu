@@ -9,6 +9,7 @@
 //   * accumulator read-back with tcgen05.ld 32x32b.
 // A second micro-benchmark measures SFU (MUFU) throughput of the candidate sigmoid formulations.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -533,14 +534,25 @@ int umma_selftest(char* report, size_t cap) {
       {"A TMEM K128, B MN sw64 N32",      {32, 128, 3, 1, 128, 64, 0}},
       {"A TMEM K128, B MN sw128 N128",    {128, 128, 3, 1, 128, 128, 0}},
       {"A TMEM K64, B K sw128 N128",      {128, 64, 3, 0, 128, 128, 0}},
-      // mixed operand formats: A fp16 (P / dS of the attention kernels), B bf16
+  };
+  // Probe (only with HSTU_SELFTEST_MIXED=1, run it in a process of its own): A fp16 x B bf16 in ONE kind::f16 instruction.
+  // The instruction descriptor has separate a_format / b_format fields, but the hardware rejects the combination with
+  // "illegal instruction" (which poisons the CUDA context), so the attention kernels convert their operands to one format.
+  const Case mixed_cases[] = {
       {"A f16 TMEM K128, B bf16 MN sw64",  {32, 128, 3, 1, 128, 64, 0, 1}},
-      {"A f16 TMEM K128, B bf16 MN sw128", {128, 128, 3, 1, 128, 128, 0, 1}},
-      {"A f16 manual K128, B bf16 MN sw64", {32, 128, 2, 1, 128, 64, 0, 1}},
-      {"A f16 MN sw128, B bf16 MN sw64",   {32, 128, 1, 1, 128, 64, 0, 1}},
-      {"A f16 MN sw128, B bf16 MN sw128",  {128, 128, 1, 1, 128, 128, 0, 1}},
       {"A f16 K sw128, B bf16 K sw128",    {128, 128, 0, 0, 128, 128, 0, 1}},
   };
+  if (const char* env = getenv("HSTU_SELFTEST_MIXED"); env && env[0] == '1') {
+    for (const Case& c : mixed_cases) {
+      int r = run_gemm_case(c.name, c.cfg, report, cap);
+      if (r == -1000) {
+        rep(report, cap, "mixed fp16 x bf16 operands: rejected by the hardware (CUDA error above); probe ends here\n");
+        return 0;
+      }
+      rep(report, cap, "mixed fp16 x bf16 operands: %s\n", r == 0 ? "ACCEPTED and exact" : "accepted but WRONG");
+    }
+    return 0;
+  }
   int fails = 0;
   for (const Case& c : cases) {
     int r = run_gemm_case(c.name, c.cfg, report, cap);

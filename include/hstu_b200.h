@@ -24,6 +24,8 @@
  *   hstu_jagged_concat / hstu_jagged_split
  *        ops/jagged_tensors.py:55-207, ops/pytorch/pt_jagged_tensors.py:31-246,
  *        ops/triton/triton_jagged_tensors.py:31-142
+ *   hstu_position_embeddings_fwd / _bwd
+ *        ops/position.py:43-96, ops/pytorch/pt_position.py:39-134, ops/triton/triton_position.py:58-435
  *   hstu_mask_valid / hstu_kv_tile_range (host-side helpers, no GPU needed)
  *        ops/pytorch/pt_hstu_attention.py:33-84 (_get_valid_attn_mask)
  */
@@ -180,6 +182,24 @@ int hstu_jagged_concat(const void* left, const void* right, void* out, const voi
 int hstu_jagged_split(const void* in, void* left, void* right, const void* offsets_left, const void* offsets_right,
                       int32_t offsets_are_i64, int32_t batch, int32_t dense_len_left, int32_t dense_len_right,
                       int32_t n_prefix, int32_t D, int32_t elem_bytes, int32_t max_seq_len, void* cuda_stream);
+
+/* Timestamp + position embedding add in front of the STU stack (ops/position.py:43-96, ops/pytorch/pt_position.py:39-134):
+ *   out[r] = cast(seq[r] * alpha) + cast(pos_w[pos_ind(r)] + ts_w[ts_bucket(r)])       (tables fp32, activations `dtype`)
+ * pos_ind / ts_bucket as the eager code computes them (see csrc/position.cu); they are also written to pos_inds / ts_inds
+ * ([total_rows] int32, nullable) for the backward.  timestamps: [total_rows] int64 (jagged).  num_time_buckets is the clamp
+ * the caller wants (the eager path uses ts_w.size(1) - 1).  log_time_bucket: 1 = log, 0 = sqrt.                        */
+int hstu_position_embeddings_fwd(const void* seq_embeddings, void* out, const float* pos_w, const float* ts_w,
+                                 const void* seq_offsets, const void* seq_lengths, const void* num_targets,
+                                 const int64_t* timestamps, int32_t* pos_inds, int32_t* ts_inds, int64_t total_rows,
+                                 int32_t batch, int32_t D, int32_t max_pos_ind, int32_t num_time_buckets,
+                                 int32_t max_contextual_seq_len, float alpha, int32_t interleave_targets,
+                                 int32_t log_time_bucket, int32_t offsets_are_i64, int32_t lengths_are_i64,
+                                 int32_t num_targets_are_i64, int32_t dtype, void* cuda_stream);
+/* d_seq = dout * alpha; d_pos_w[pos_inds[r]] += dout[r]; d_ts_w[ts_inds[r]] += dout[r] (fp32 tables, zero-initialised by the
+ * caller, accumulated with atomics).                                                                                     */
+int hstu_position_embeddings_bwd(const void* dout, void* d_seq_embeddings, float* d_pos_w, float* d_ts_w,
+                                 const int32_t* pos_inds, const int32_t* ts_inds, int64_t total_rows, int32_t D, float alpha,
+                                 int32_t dtype, void* cuda_stream);
 
 /* On-device self test of the tcgen05 / TMA primitives the attention kernels are built from (K-major and MN-major
  * shared-memory descriptors, TMEM load/store).  Writes a report into `report` (host buffer).  Returns the number

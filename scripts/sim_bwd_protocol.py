@@ -7,8 +7,9 @@ phases behind (its parity test would then block until the barrier wraps).  Both 
 development (unit_done with a 3-slot ring; s_full with a single slot); this model reproduces them when the fix is removed
 (--break-ud / --break-sf).
 
-Actors: P producer, X (scores), Y (dV), Z (dK, dQ), W0 / W1 elementwise warpgroups.  tcgen05.commit and TMA completions are
-asynchronous: they are queued per issuing actor and fire later, in order.
+Actors: X (scores), YV (dV), YK (dK), Z (dQ) issuers, W0 / W1 elementwise warpgroups, D the dQ drain warpgroup whose elected
+lane is also the TMA producer.  tcgen05.commit and TMA completions are asynchronous: they are queued per issuing actor and
+fire later, in order.
 usage: sim_bwd_protocol.py [--d 32|64|128] [--tiles T] [--seeds N] [--break-ud] [--break-sf]"""
 import argparse, random
 
@@ -40,13 +41,13 @@ def run(T, d, seed, break_ud=False, break_sf=False):
     B = {"kv": Bar(1), "fin": Bar(2)}
     for i in range(4):
         B[f"qf{i}"] = Bar(1)
-        B[f"td{i}"] = Bar(2)
+        B[f"td{i}"] = Bar(3)       # YV, YK, Z
         B[f"ud{i}"] = Bar(1)       # count 128 threads modelled as one arrival per warpgroup
     for i in range(3):
         B[f"sf{i}"] = Bar(1)
         B[f"free{i}"] = Bar(1)
     for i in range(2):
-        B[f"dqe{i}"] = Bar(2)      # both warpgroups
+        B[f"dqe{i}"] = Bar(1)      # the drain warpgroup (128 threads modelled as one arrival)
     U = 2 * T
 
     def ud(u):  # barrier instance and phase index of unit_done for unit u
@@ -54,13 +55,6 @@ def run(T, d, seed, break_ud=False, break_sf=False):
         if break_ud:
             return f"ud{hf}", i                     # one barrier per half: aliases with a 3-slot ring
         return f"ud{hf * 2 + (i & 1)}", i >> 1
-
-    def producer():
-        yield ("async", "kv")
-        for i in range(T):
-            if i >= NST:
-                yield ("wait", f"td{(i - NST) & 3}", (i - NST) >> 2)
-            yield ("async", f"qf{i % NST}")
 
     def X():
         yield ("wait", "kv", 0)
@@ -72,7 +66,7 @@ def run(T, d, seed, break_ud=False, break_sf=False):
                 yield ("wait", f"qf{i % NST}", i // NST)
             yield ("async", f"sf{u % NSF}")
 
-    def Y():
+    def YV():
         for u in range(U):
             i, hf = u >> 1, u & 1
             yield ("wait",) + ud(u)
@@ -81,33 +75,43 @@ def run(T, d, seed, break_ud=False, break_sf=False):
                 yield ("async", f"td{i & 3}")
         yield ("async", "fin")
 
-    def Z():
+    def YK():
         for u in range(U):
             i, hf = u >> 1, u & 1
             yield ("wait",) + ud(u)
             if hf == 1:
-                if i >= NDQ:
-                    yield ("wait", f"dqe{i % NDQ}", i // NDQ - 1)
                 yield ("async", f"td{i & 3}")
         yield ("async", "fin")
 
+    def Z():
+        yield ("wait", "kv", 0)
+        for i in range(T):
+            yield ("wait",) + ud(2 * i)
+            yield ("wait",) + ud(2 * i + 1)
+            if i >= NDQ:
+                yield ("wait", f"dqe{i % NDQ}", i // NDQ - 1)
+            yield ("async", f"td{i & 3}")
+
     def W(h):
-        def drain(i):
-            yield ("wait", f"td{i & 3}", i >> 2)
-            yield ("arrive", f"dqe{i % NDQ}")
         for i in range(T):
             u = 2 * i + h
             yield ("wait", f"sf{u % NSF}", u // NSF)
             if i >= 2:
                 yield ("wait", f"td{(i - 2) & 3}", (i - 2) >> 2)
             yield ("arrive", ud(u)[0])
-            if i >= LAG:
-                yield from drain(i - LAG)
-        for t in range(max(0, T - LAG), T):
-            yield from drain(t)
         yield ("wait", "fin", 0)
 
-    actors = {"P": producer(), "X": X(), "Y": Y(), "Z": Z(), "W0": W(0), "W1": W(1)}
+    def Dr():
+        yield ("async", "kv")
+        for i in range(min(NST, T)):
+            yield ("async", f"qf{i % NST}")
+        for i in range(T):
+            yield ("wait", f"td{i & 3}", i >> 2)
+            if i + NST < T:
+                yield ("async", f"qf{(i + NST) % NST}")
+            yield ("arrive", f"dqe{i % NDQ}")
+
+    actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W0": W(0), "W1": W(1), "D": Dr()}
     pending = {k: None for k in actors}     # the blocking wait of each actor
     queues = {k: [] for k in actors}        # asynchronous completions (commit / TMA), in order per actor
     done = set()

@@ -1,6 +1,6 @@
 """Summarise gpurun_out/bwd_trace.txt (HSTU_TRACE build of the backward kernel, CTA (0,0,0)): merged event timeline in clocks.
 
-roles: 0 = issuer X (scores), 1 = issuer Y (dV), 4 = issuer Z (dK, dQ), 2/3 = elementwise warpgroups 0/1.
+roles: 0 = issuer X (scores), 1 = issuer YV (dV), 4 = issuer YK (dK), 2/3 = elementwise warpgroups 0/1.
 usage: trace_report.py [trace] [first_unit] [n_units]"""
 import collections, sys
 path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/bwd_trace.txt"
@@ -16,15 +16,15 @@ for u in range(u0, u0 + nu):
     a = rows[0].get(u)
     if a: ev += [(a[0] - t0, f'X  u{u} waits slot_free / q_full'), (a[1] - t0, f'X  u{u} issues S^T, dP^T'), (a[2] - t0, f'X  u{u} commit issued')]
     a = rows[1].get(u)
-    if a: ev += [(a[0] - t0, f'Y  u{u} waits unit_done'), (a[1] - t0, f'Y  u{u} issues dV'), (a[2] - t0, f'Y  u{u} commits issued')]
-    a = rows[4].get(u) or rows[4].get(u // 2)
-    if a: ev += [(a[0] - t0, f'Z  u{u} waits unit_done'), (a[1] - t0, f'Z  u{u} issues dK/dQ'), (a[2] - t0, f'Z  u{u} issued')]
+    if a: ev += [(a[0] - t0, f'YV u{u} waits unit_done'), (a[1] - t0, f'YV u{u} issues dV'), (a[2] - t0, f'YV u{u} commits issued')]
+    a = rows[4].get(u)
+    if a: ev += [(a[0] - t0, f'YK u{u} waits unit_done'), (a[1] - t0, f'YK u{u} issues dK'), (a[2] - t0, f'YK u{u} issued')]
 for wg in (0, 1):
     for i in range(u0 // 2, (u0 + nu) // 2 + 1):
         a = rows[2 + wg].get(i)
         if a:
             u = 2 * i + wg
             ev += [(a[0] - t0, f'W{wg} u{u} waits s_full'), (a[1] - t0, f'W{wg} u{u} elementwise starts'),
-                   (a[2] - t0, f'W{wg} u{u} arrives unit_done, drains dQ'), (a[3] - t0, f'W{wg} u{u} drain done')]
+                   (a[2] - t0, f'W{wg} u{u} arrives unit_done')]
 for t, e in sorted(set(ev)):
     print(f'{t:8d}  {e}')
