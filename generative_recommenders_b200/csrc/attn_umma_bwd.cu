@@ -100,6 +100,7 @@ struct BwdCfg {
 struct BwdBars {
   uint64_t kv_full;
   uint64_t q_full[4];
+  uint64_t kv_ready, q_ready[4];  // bf16 inputs: the tiles have been converted to fp16 in place (128 threads of the drain warpgroup)
   uint64_t s_full[3], unit_done[4];
   uint64_t tile_done[4];  // tile i -> [i % 4]: both issuers have finished every GEMM of query tile i (count 2)
   uint64_t slot_free[3];  // unit u -> [u % NSLOT]: dV of the unit has consumed P^T in the slot
@@ -165,10 +166,6 @@ __global__ void dout_amax_kernel(const uint16_t* __restrict__ dout, long long ro
   }
 }
 
-template <int NREG>
-__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NREG)); }
-template <int NREG>
-__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NREG)); }
 __device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // 512 threads = 4 warpgroups with their own register budgets (setmaxnreg; 128 regs / thread at launch):
@@ -180,6 +177,10 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
   using Cfg = BwdCfg<D>;
   constexpr int SW = Cfg::SW;
   constexpr int NST = Cfg::STAGES;
+  // bf16 inputs: every TMA-landed tile (K, V, Q_i, dO_i) is converted to fp16 in place in shared memory (dO times the power of
+  // two 2^-e, e = floor(log2 max|dO|), so that dP, dS, dK, dQ and dV all carry that factor until their epilogues) and ALL MMAs of
+  // the kernel run fp16 x fp16.  fp16 inputs skip the conversion; there the factor enters through the dS constants instead.
+  constexpr bool CONV = BF16;
   const int b = blockIdx.z, h = blockIdx.y;
   const int n0 = (int)blockIdx.x * 128;
   const long long row0 = load_index(p.seq_offsets, p.offsets_i64, b);
@@ -225,6 +226,8 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     for (int i = 0; i < 4; ++i) mbar_init(&bars->unit_done[i], 128);
     for (int i = 0; i < 2; ++i) mbar_init(&bars->dq_empty[i], 128);
     mbar_init(&bars->fin_full, 2);         // YV (dV) and YK (dK)
+    mbar_init(&bars->kv_ready, 128);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars->q_ready[i], 128);
     for (int i = 0; i < 3; ++i) mbar_init(&bars->slot_free[i], 1);
     fence_barrier_init();
   }
@@ -233,6 +236,9 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
+  uint64_t* const kv_rdy = CONV ? &bars->kv_ready : &bars->kv_full;
+  uint64_t* const q_rdy = CONV ? bars->q_ready : bars->q_full;
+  const float ds_scale = ds_scale_from_amax(__ldg(p.dout_amax_bits));  // 2^-e
 
   if (warp < 4) {
     reg_dealloc<64>();
@@ -249,12 +255,12 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     const bool leader = lane == 0;
     const int U = 2 * T;
     if (warp == 0) {
-      constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, BF16, BF16);    // S^T, dP^T half-tiles
+      constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, false, false);  // S^T, dP^T half-tiles (fp16 x fp16)
       const uint64_t dk_k = desc_kmajor<SW>(smem_u32(sK), 0);                        // K as K-major A (S^T)
       const uint64_t dv_k = desc_kmajor<SW>(smem_u32(sV), 0);                        // V as K-major A (dP^T)
       const uint64_t dq_k = desc_kmajor<SW>(smem_u32(sQ), 0);                        // Q_i rows as K-major B
       const uint64_t ddo_k = desc_kmajor<SW>(smem_u32(sDO), 0);                      // dO_i rows as K-major B
-      mbar_wait(&bars->kv_full, 0);
+      mbar_wait(kv_rdy, 0);
       tc_fence_after_sync();
       for (int u = 0; u < U; ++u) {
         const int i = u >> 1, hf = u & 1, st = i % NST, slot = u % NSLOT;
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
           tc_fence_after_sync();
         }
         if (hf == 0) {
-          mbar_wait(&bars->q_full[st], (i / NST) & 1);
+          mbar_wait(&q_rdy[st], (i / NST) & 1);
           tc_fence_after_sync();
         }
         // query rows [64 hf, 64 hf + 64) of the staged Q_i / dO_i tiles
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       }
     } else if (warp == 1) {
       // ---- issuer YV: dV += P^T dO (A = P^T from the unit's TMEM slot) of every unit; its commit frees the slot ----
-      constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // A = P^T from TMEM, B MN-major
+      constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, false, false);   // A = P^T from TMEM, B MN-major (fp16 x fp16)
       const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
       for (int u = 0; u < U; ++u) {
         const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1, slot = u % NSLOT;
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       __syncwarp();
     } else if (warp == 2) {
       // ---- issuer YK: dK += dS^T Q (A = the unit's dS^T box in shared memory) of every unit ----
-      constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, BF16, BF16);     // A = dS^T K-major, B MN-major
+      constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, false, false);   // A = dS^T K-major, B MN-major (fp16 x fp16)
       const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box [kv][q] as K-major A
       const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
       for (int u = 0; u < U; ++u) {
@@ -343,10 +349,10 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       __syncwarp();
     } else {
       // ---- issuer Z: dQ_i = dS_i K (A = the dS^T box pair read MN-major, M = 128 query rows) of every query tile ----
-      constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, BF16, BF16);      // A = dS^T MN-major, B MN-major
+      constexpr uint32_t idesc_dq = make_idesc(128, D, true, true, false, false);    // A = dS^T MN-major, B MN-major (fp16 x fp16)
       const uint64_t dds_mn = desc_mnmajor<128>(smem_u32(sDST), 0, 16384);           // the box pair as MN-major A
       const uint64_t dk_mn = desc_mnmajor<SW>(smem_u32(sK), 0, Cfg::BOX_BYTES);      // K as MN-major B
-      mbar_wait(&bars->kv_full, 0);
+      mbar_wait(kv_rdy, 0);
       for (int i = 0; i < T; ++i) {
         const int pb = i & 1;
         mbar_wait(&bars->unit_done[0 * 2 + pb], (i >> 1) & 1);
@@ -400,6 +406,23 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       }
       for (int i = 0; i < NST && i < T; ++i) load_tile(i);
     }
+    const int ct = tid - 384;  // index inside this warpgroup
+    auto convert_tile = [&](int i) {  // Q_i (as is) and dO_i (times 2^-e) of stage i % NST: bf16 -> fp16 in place
+      const int st = i % NST;
+      mbar_wait(&bars->q_full[st], (i / NST) & 1);
+      convert_bf16_to_f16_inplace<128>(sQ + st * Cfg::TILE_BYTES, Cfg::TILE_BYTES, ct, 1.0f);
+      convert_bf16_to_f16_inplace<128>(sDO + st * Cfg::TILE_BYTES, Cfg::TILE_BYTES, ct, ds_scale);
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->q_ready[st]);
+    };
+    if (CONV) {
+      mbar_wait(&bars->kv_full, 0);
+      convert_bf16_to_f16_inplace<128>(sK, Cfg::TILE_BYTES, ct, 1.0f);
+      convert_bf16_to_f16_inplace<128>(sV, Cfg::TILE_BYTES, ct, 1.0f);
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->kv_ready);
+      for (int i = 0; i < NST && i < T; ++i) convert_tile(i);
+    }
     int box = 0;  // staging box counter (box & 1 = buffer)
     for (int i = 0; i < T; ++i) {
       mbar_wait(&bars->tile_done[i & 3], (i >> 2) & 1);
@@ -430,6 +453,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
           bulk_commit_group();
         }
       }
+      if (CONV && i + NST < T) convert_tile(i + NST);  // the load issued above: by now most of its latency has passed
     }
     if (elected) bulk_wait_group_read0();          // shared memory must stay valid until the last reduce has read it
   } else {
@@ -441,11 +465,11 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
     const int j_pos = n0 + row;
     const float2 ah2 = make_float2(p.alpha_half, p.alpha_half);
-    // dS^T is an fp16 tensor-core operand (see the header comment): it is stored as dS * 2^-e with e = floor(log2 max|dO|),
-    // the power of two is folded into the constants of the sigmoid-derivative polynomial, and removed again in the dK epilogue
-    // and in dq_convert_kernel.
-    const float ds_scale = ds_scale_from_amax(__ldg(p.dout_amax_bits));
-    const float2 shalf2v = make_float2(0.5f * ds_scale, 0.5f * ds_scale), nshalf2v = make_float2(-0.5f * ds_scale, -0.5f * ds_scale);
+    // dS^T is an fp16 tensor-core operand: it is stored as dS * 2^-e.  With bf16 inputs the factor is already in dO (applied
+    // when dO was converted); with fp16 inputs it is folded into the constants of the sigmoid-derivative polynomial here.
+    // It is removed again in the dK / dV epilogues and in dq_convert_kernel.
+    const float ew_scale = CONV ? 1.0f : ds_scale;
+    const float2 shalf2v = make_float2(0.5f * ew_scale, 0.5f * ew_scale), nshalf2v = make_float2(-0.5f * ew_scale, -0.5f * ew_scale);
     const bool fast = msk.fast != 0;
     const bool j_ok = j_pos < len;
     const bool j_hist = j_ok && (!msk.has_tgt || j_pos < msk.max_id);  // fast mask: valid = (j_hist & i > j) | (i == j)
@@ -492,8 +516,8 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
           for (int e = 0; e < 32; e += 2) {
             float p0, p1, d0, d1;
             HSTU_BWD_ELEM2(e, p0, p1, d0, d1);
-            pp[e >> 1] = pack_operand<BF16>(p0, p1);
-            dd[e >> 1] = pack_operand<BF16>(d0, d1);
+            pp[e >> 1] = pack_f16x2_sat(p0, p1);
+            dd[e >> 1] = pack_f16x2_sat(d0, d1);
           }
         } else if (mode == 1) {
           // valid(i, j) = ((j is history) & (i > j)) | (i == j), restricted to i < len and j < len
@@ -508,8 +532,8 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
             const bool v1 = ((c0 + 1 > lo_c) | (c0 + 1 == dg_c)) & (c0 + 1 < len_rel);
             p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;
             p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;
-            pp[e >> 1] = pack_operand<BF16>(p0, p1);
-            dd[e >> 1] = pack_operand<BF16>(d0, d1);
+            pp[e >> 1] = pack_f16x2_sat(p0, p1);
+            dd[e >> 1] = pack_f16x2_sat(d0, d1);
           }
         } else {
 #pragma unroll
@@ -521,8 +545,8 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
             const bool v1 = j_ok && i_pos + 1 < len && mask_valid(msk, i_pos + 1, j_pos);
             p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;
             p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;
-            pp[e >> 1] = pack_operand<BF16>(p0, p1);
-            dd[e >> 1] = pack_operand<BF16>(d0, d1);
+            pp[e >> 1] = pack_f16x2_sat(p0, p1);
+            dd[e >> 1] = pack_f16x2_sat(d0, d1);
           }
         }
 #undef HSTU_BWD_ELEM2
@@ -544,7 +568,8 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     mbar_wait(&bars->fin_full, 0);
     tc_fence_after_sync();
     const uint32_t acc = tmem + (wg == 0 ? Cfg::TMEM_DV : Cfg::TMEM_DK) + lane_bits;
-    const float scale = wg == 0 ? p.dv_scale : p.dk_scale / ds_scale;  // ds_scale is a power of two: exact
+    // undo 2^-e (a power of two: exact): dK always carries it, dV only when dO itself was scaled
+    const float scale = wg == 0 ? (CONV ? p.dv_scale / ds_scale : p.dv_scale) : p.dk_scale / ds_scale;
     uint16_t* gptr = wg == 0
         ? reinterpret_cast<uint16_t*>(p.dv) + (row0 + j_pos) * p.dv_row_stride + (long long)h * p.dv_head_stride
         : reinterpret_cast<uint16_t*>(p.dk) + (row0 + j_pos) * p.dk_row_stride + (long long)h * p.dk_head_stride;

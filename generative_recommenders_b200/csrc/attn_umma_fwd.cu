@@ -13,6 +13,10 @@
 //   warps 4-7, 8-11: two "silu" warpgroups.  Warpgroup g owns key tiles t = g, g+2, ...: tcgen05.ld S (one query row per
 //                    thread, next 32 columns prefetched), p = silu(alpha*s) * mask via one MUFU (tanh) + packed fp32x2
 //                    FMUL2 / FFMA2, packs bf16 pairs and writes them with tcgen05.st over the S columns already read.
+//   warps 12-15    : (bf16 inputs only) converter warpgroup: kind::f16 needs ONE operand format per instruction and the parity
+//                    budget needs P in fp16 (11-bit significand; a bf16 P alone costs 1.7e-3 of relative error), so bf16 Q / K / V
+//                    tiles are converted to fp16 IN PLACE in shared memory when their TMA load lands (exact for every bf16
+//                    value in the fp16 range) and all MMAs of the kernel run on fp16 operands.  fp16 inputs skip this stage.
 // The 1/N factor of the reference is applied once in the epilogue (O tile: TMEM -> registers -> 128-bit global stores,
 // rows past the sequence end are not written).  Rows of neighbouring sequences that a 128-row TMA box drags in are
 // neutralised by the mask (P = 0 for key positions >= len), never by re-reading memory.
@@ -65,14 +69,16 @@ struct FwdCfg {
 struct FwdBars {
   uint64_t q_full;
   uint64_t k_full[3], v_full[3];
+  uint64_t q_ready, k_ready[3], v_ready[3];  // bf16 inputs: the tile has been converted to fp16 (128 converter threads)
   uint64_t s_full[3], p_full[3], pv_done[3];
   uint64_t o_full;
   uint32_t tmem_base;
 };
 
 template <int D, bool BF16>
-__global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(const __grid_constant__ FwdParams p) {
   using Cfg = FwdCfg<D>;
+  constexpr bool CONV = BF16;  // bf16 tiles are converted to fp16 in shared memory; every MMA below is fp16 x fp16
   constexpr int SW = Cfg::SW;
   constexpr int NST = Cfg::STAGES;
   const int b = blockIdx.z, h = blockIdx.y;
@@ -108,7 +114,10 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
       mbar_init(&bars->s_full[i], 1);
       mbar_init(&bars->p_full[i], 128);
       mbar_init(&bars->pv_done[i], 1);
+      mbar_init(&bars->k_ready[i], 128);
+      mbar_init(&bars->v_ready[i], 128);
     }
+    mbar_init(&bars->q_ready, 128);
     mbar_init(&bars->o_full, 1);
     fence_barrier_init();
   }
@@ -117,8 +126,33 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
+  uint64_t* const q_rdy = CONV ? &bars->q_ready : &bars->q_full;
+  uint64_t* const k_rdy = CONV ? bars->k_ready : bars->k_full;
+  uint64_t* const v_rdy = CONV ? bars->v_ready : bars->v_full;
+  // bf16 inputs run 512 threads (128 registers / thread at launch): per-warpgroup budgets are set at the top of each role
 
-  if (warp == 0) {
+  if (warp >= 12) {
+    // ---------------- converter warpgroup (bf16 inputs): TMA-landed tile -> fp16 in place -> ready ----------------
+    reg_dealloc<64>();
+    const int t = tid - 384;
+    mbar_wait(&bars->q_full, 0);
+    convert_bf16_to_f16_inplace<128>(sQ, Cfg::TILE_BYTES, t, 1.0f);
+    fence_proxy_async_smem();
+    mbar_arrive(&bars->q_ready);
+    for (int i = 0; i < T; ++i) {
+      const int st = i % NST;
+      mbar_wait(&bars->k_full[st], (i / NST) & 1);
+      convert_bf16_to_f16_inplace<128>(sK + st * Cfg::TILE_BYTES, Cfg::TILE_BYTES, t, 1.0f);
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->k_ready[st]);
+      mbar_wait(&bars->v_full[st], (i / NST) & 1);
+      convert_bf16_to_f16_inplace<128>(sV + st * Cfg::TILE_BYTES, Cfg::TILE_BYTES, t, 1.0f);
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->v_ready[st]);
+    }
+  } else if (warp < 4) {
+   if (CONV) reg_dealloc<80>();
+   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer: Q, then K tiles ----------------
       prefetch_tensormap(&p.tmQ);
@@ -171,14 +205,14 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
     // descriptors are built once and only their address field is advanced.  One commit per tile and thread: K / V stages
     // are released through the slot barriers (stage = slot = tile % 3).
     const bool leader = lane == 0;
-    constexpr uint32_t idesc_qk = make_idesc(128, 128, false, false, BF16, BF16);
+    constexpr uint32_t idesc_qk = make_idesc(128, 128, false, false, false, false);  // fp16 x fp16 (see the header comment)
     const uint64_t dq0 = desc_kmajor<SW>(smem_u32(sQ), 0);
     const uint64_t dk0 = desc_kmajor<SW>(smem_u32(sK), 0);
-    mbar_wait(&bars->q_full, 0);
+    mbar_wait(q_rdy, 0);
     for (int i = 0; i < T; ++i) {
       const int st = i % 3;
       if (i >= 3) mbar_wait(&bars->pv_done[st], ((i / 3) - 1) & 1);  // P_{i-3} (front of this slot) has been consumed
-      mbar_wait(&bars->k_full[st], (i / 3) & 1);
+      mbar_wait(&k_rdy[st], (i / 3) & 1);
       tc_fence_after_sync();
       const uint64_t kd = dk0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
       const uint32_t ts = tmem + Cfg::TMEM_S + st * 128;
@@ -196,12 +230,12 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
   } else if (warp == 2) {
     // ---------------- MMA issuer 2: O += P_i V_i (A = P from TMEM, B = V read MN-major) ----------------
     const bool leader = lane == 0;
-    constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, BF16, BF16);
+    constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, false, false);     // P (TMEM) and V both fp16
     const uint64_t dv0 = desc_mnmajor<SW>(smem_u32(sV), 0, Cfg::BOX_BYTES);
     for (int i = 0; i < T; ++i) {
       const int st = i % 3;
       mbar_wait(&bars->p_full[st], (i / 3) & 1);   // P_i sits in TMEM (front of score slot i % 3)
-      mbar_wait(&bars->v_full[st], (i / 3) & 1);
+      mbar_wait(&v_rdy[st], (i / 3) & 1);
       tc_fence_after_sync();
       const uint64_t vd = dv0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
       const uint32_t tp = tmem + Cfg::TMEM_S + st * 128;
@@ -216,8 +250,10 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
     }
     if (leader) mma_commit(&bars->o_full);
     __syncwarp();
-  } else if (warp >= 4) {
+   }
+  } else {
     // ---------------- silu warpgroups ----------------
+    if (CONV) reg_alloc<168>();
     const int wg = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;              // query row inside the tile == TMEM lane
@@ -256,7 +292,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
             const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), ah2);
             const float2 pv = __ffma2_rn(hh, make_float2(tanh_approx(hh.x), tanh_approx(hh.y)), hh);
             const float p0 = pv.x, p1 = pv.y;
-            pk[e >> 1] = pack_operand<BF16>(p0, p1);
+            pk[e >> 1] = pack_f16x2_sat(p0, p1);
           }
         } else if (mode == 1) {
 #pragma unroll
@@ -267,7 +303,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
             float p0 = pv.x, p1 = pv.y;
             p0 = ((j0 < lim_rel) | (j0 == diag_rel)) ? p0 : 0.f;
             p1 = ((j0 + 1 < lim_rel) | (j0 + 1 == diag_rel)) ? p1 : 0.f;
-            pk[e >> 1] = pack_operand<BF16>(p0, p1);
+            pk[e >> 1] = pack_f16x2_sat(p0, p1);
           }
         } else {
 #pragma unroll
@@ -278,7 +314,7 @@ __global__ void __launch_bounds__(384, 1) attn_fwd_umma_kernel(const __grid_cons
             float p0 = pv.x, p1 = pv.y;
             p0 = (j < len && mask_valid(msk, i_pos, j)) ? p0 : 0.f;
             p1 = (j + 1 < len && mask_valid(msk, i_pos, j + 1)) ? p1 : 0.f;
-            pk[e >> 1] = pack_operand<BF16>(p0, p1);
+            pk[e >> 1] = pack_f16x2_sat(p0, p1);
           }
         }
         // P chunk c (32 bf16 = 16 columns) goes to columns [16 c, 16 c + 16) of the slot: a region of S that has already
@@ -378,7 +414,7 @@ static int launch_fwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   auto kern = attn_fwd_umma_kernel<D, BF16>;
   HSTU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   dim3 grid((p.max_seq_len + 127) / 128, p.heads, p.batch);
-  kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(fp);
+  kern<<<grid, BF16 ? 512 : 384, Cfg::SMEM_BYTES, st>>>(fp);
   HSTU_CUDA_OK(cudaGetLastError());
   return 0;
 }

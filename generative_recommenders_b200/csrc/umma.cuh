@@ -264,6 +264,29 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// In-place bf16 -> fp16 conversion (times `scale`, a power of two) of `bytes` bytes of shared memory by NT threads (t = index
+// of the calling thread).  Elementwise and in place, so it is independent of the swizzled tile layout.  fp16 holds every bf16
+// significand exactly; magnitudes above 65504 saturate and magnitudes below 2^-24 flush to zero.
+template <int NT>
+__device__ __forceinline__ void convert_bf16_to_f16_inplace(uint8_t* base, int bytes, int t, float scale) {
+  const uint32_t s0 = smem_u32(base);
+  for (int off = t * 16; off < bytes; off += NT * 16) {
+    uint32_t w[4];
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(s0 + off));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float lo = __uint_as_float(w[i] << 16) * scale, hi = __uint_as_float(w[i] & 0xffff0000u) * scale;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(hi), "f"(lo));
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + off), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+  }
+}
+
+template <int NREG>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NREG)); }
+template <int NREG>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NREG)); }
+
 // 16-bit tensor-core operand pair in the format the kernel's MMAs use (kind::f16 needs the SAME format for A and B: a mixed
 // fp16 x bf16 instruction descriptor raises "illegal instruction" on B200 -- umma_selftest reports the probe)
 template <bool OP_BF16>

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY -- pure-torch stand-ins for the three `torch.ops.fbgemm.*`
-jagged ops the reference's PyTorch-eager path calls.
+jagged ops the reference's PyTorch-eager path calls (plus `jagged_dense_elementwise_add_jagged_output` for ops/position.py).
 
 The reference (generative_recommenders @ 2e81fab) depends on `fbgemm_gpu>=1.1.0`
 (/root/reference/requirements.txt:2), which is a third-party dependency that is NOT
@@ -66,6 +66,16 @@ def _dense_to_jagged(
     return values, [x_offsets[0]]
 
 
+def _jagged_dense_elementwise_add_jagged_output(
+    x_values: torch.Tensor, x_offsets: List[torch.Tensor], y: torch.Tensor
+) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    # x_values [L, D] jagged by x_offsets; y dense [B, N, D]: out[row of (b, n)] = x_values[row] + y[b, n]
+    # (call site: ops/pytorch/pt_position.py:130-134)
+    assert len(x_offsets) == 1
+    picked, _ = _dense_to_jagged(y, x_offsets)
+    return x_values + picked, [x_offsets[0]]
+
+
 def _asynchronous_complete_cumsum(t_in: torch.Tensor) -> torch.Tensor:
     out = torch.zeros(t_in.numel() + 1, dtype=t_in.dtype, device=t_in.device)
     out[1:] = torch.cumsum(t_in, dim=0)
@@ -93,6 +103,11 @@ def install() -> None:
         "-> (Tensor, Tensor[])"
     )
     lib.define("asynchronous_complete_cumsum(Tensor t_in) -> Tensor")
+    lib.define(
+        "jagged_dense_elementwise_add_jagged_output(Tensor x_values, Tensor[] x_offsets, Tensor y) -> (Tensor, Tensor[])"
+    )
+    lib.impl("jagged_dense_elementwise_add_jagged_output", _jagged_dense_elementwise_add_jagged_output,
+             "CompositeImplicitAutograd")
     lib.impl("jagged_to_padded_dense", _jagged_to_padded_dense, "CompositeImplicitAutograd")
     lib.impl("dense_to_jagged", _dense_to_jagged, "CompositeImplicitAutograd")
     lib.impl("asynchronous_complete_cumsum", _asynchronous_complete_cumsum, "CompositeImplicitAutograd")

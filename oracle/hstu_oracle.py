@@ -388,6 +388,67 @@ def stu_layer_fwd(
 
 
 # --------------------------------------------------------------------------------------
+# timestamp + position embedding add  -- ops/position.py:43-96, ops/pytorch/pt_position.py:39-134
+# --------------------------------------------------------------------------------------
+
+
+def position_indices(seq_offsets, seq_lengths, timestamps, num_targets, max_contextual_seq_len, max_pos_ind,
+                     num_time_buckets, interleave_targets, time_bucket_fn):
+    """Integer part of the op, per jagged row: (pos_ind [L] int64, ts_bucket [L] int64).
+
+    pos_ind: pt_position.py:39-72 (_get_col_indices) for the real positions of each sequence.
+    ts_bucket: pt_position.py:97-123 -- query time = timestamp of row len-1 (index clamped to >= 0 of the zero-padded row),
+    dt -> float32 (torch promotes the int64 clamp(min=1e-6) to float32), /60, log|sqrt, clamp(min=0).int(), clamp to
+    [0, num_time_buckets]."""
+    off = _lens(seq_offsets)
+    lens = seq_lengths.detach().cpu().numpy().astype(np.int64)
+    ts = timestamps.detach().cpu().numpy().astype(np.int64)
+    nt = None if num_targets is None else num_targets.detach().cpu().numpy().astype(np.int64)
+    L = int(off[-1])
+    pos = np.zeros(L, dtype=np.int64)
+    bkt = np.zeros(L, dtype=np.int64)
+    for b in range(len(off) - 1):
+        s, e = int(off[b]), int(off[b + 1])
+        if e <= s:
+            continue
+        n = np.arange(e - s, dtype=np.int64)
+        ln = int(lens[b])
+        if nt is not None:
+            high = ln - int(nt[b]) * (2 if interleave_targets else 1)
+            c = high - np.minimum(n, high)
+        else:
+            c = ln - n
+        c = np.minimum(c + max_contextual_seq_len, max_pos_ind - 1)
+        c = np.where(n < max_contextual_seq_len, n, c)
+        pos[s:e] = c
+        qi = max(ln - 1, 0)
+        qt = ts[s + qi] if s + qi < e else 0
+        dt = (qt - ts[s:e]).astype(np.float32)
+        x = np.maximum(dt, np.float32(1e-6)) / np.float32(60.0)
+        x = np.log(x) if time_bucket_fn == "log" else np.sqrt(x)
+        x = np.maximum(x.astype(np.float32), np.float32(0.0))
+        bkt[s:e] = np.clip(x.astype(np.int32), 0, num_time_buckets)
+    return torch.from_numpy(pos), torch.from_numpy(bkt)
+
+
+def add_timestamp_positional_embeddings(alpha, max_contextual_seq_len, pos_w, ts_w, seq_offsets, seq_lengths, seq_embeddings,
+                                        timestamps, num_targets, interleave_targets, time_bucket_fn, dout=None):
+    """out = (seq * alpha) + (pos_w[pos] + ts_w[bucket]).to(dtype) with the reference's roundings (position.py:58,
+    pt_position.py:124-133); with `dout`: also (d_seq, d_pos_w, d_ts_w) = (dout * alpha, scatter-adds of dout in fp32)."""
+    dt = seq_embeddings.dtype
+    pos, bkt = position_indices(seq_offsets, seq_lengths, timestamps, num_targets, max_contextual_seq_len, pos_w.shape[0],
+                                ts_w.shape[1] - 1, interleave_targets, time_bucket_fn)
+    emb = (ts_w.float()[bkt] + pos_w.float()[pos]).to(dt)
+    out = (seq_embeddings * alpha) + emb
+    if dout is None:
+        return out
+    g = dout.float()
+    dpos = torch.zeros(pos_w.shape, dtype=torch.float32).index_add_(0, pos, g)
+    dts = torch.zeros(ts_w.shape, dtype=torch.float32).index_add_(0, bkt, g)
+    return out, (dout * alpha), dpos, dts
+
+
+# --------------------------------------------------------------------------------------
 # jagged row routing (integer-exact)  -- ops/pytorch/pt_jagged_tensors.py
 # --------------------------------------------------------------------------------------
 

@@ -38,9 +38,10 @@ def run(T, d, seed, break_ud=False, break_sf=False):
     NSF = NSLOT if break_sf else max(NSLOT, 2)
     LAG = NDQ
     rnd = random.Random(seed)
-    B = {"kv": Bar(1), "fin": Bar(2)}
+    B = {"kv": Bar(1), "kvr": Bar(1), "fin": Bar(2)}
     for i in range(4):
         B[f"qf{i}"] = Bar(1)
+        B[f"qr{i}"] = Bar(1)       # bf16 inputs: tile converted to fp16 (128 drain threads modelled as one arrival)
         B[f"td{i}"] = Bar(3)       # YV, YK, Z
         B[f"ud{i}"] = Bar(1)       # count 128 threads modelled as one arrival per warpgroup
     for i in range(3):
@@ -57,13 +58,13 @@ def run(T, d, seed, break_ud=False, break_sf=False):
         return f"ud{hf * 2 + (i & 1)}", i >> 1
 
     def X():
-        yield ("wait", "kv", 0)
+        yield ("wait", "kvr", 0)
         for u in range(U):
             i, hf = u >> 1, u & 1
             if u >= NSLOT:
                 yield ("wait", f"free{u % NSLOT}", u // NSLOT - 1)
             if hf == 0:
-                yield ("wait", f"qf{i % NST}", i // NST)
+                yield ("wait", f"qr{i % NST}", i // NST)
             yield ("async", f"sf{u % NSF}")
 
     def YV():
@@ -84,7 +85,7 @@ def run(T, d, seed, break_ud=False, break_sf=False):
         yield ("async", "fin")
 
     def Z():
-        yield ("wait", "kv", 0)
+        yield ("wait", "kvr", 0)
         for i in range(T):
             yield ("wait",) + ud(2 * i)
             yield ("wait",) + ud(2 * i + 1)
@@ -101,15 +102,23 @@ def run(T, d, seed, break_ud=False, break_sf=False):
             yield ("arrive", ud(u)[0])
         yield ("wait", "fin", 0)
 
-    def Dr():
+    def Dr():  # the bf16 variant (with the in-place conversion); fp16 inputs are the same protocol without the qr hops
         yield ("async", "kv")
         for i in range(min(NST, T)):
             yield ("async", f"qf{i % NST}")
+        yield ("wait", "kv", 0)
+        yield ("arrive", "kvr")
+        for i in range(min(NST, T)):
+            yield ("wait", f"qf{i % NST}", i // NST)
+            yield ("arrive", f"qr{i % NST}")
         for i in range(T):
             yield ("wait", f"td{i & 3}", i >> 2)
             if i + NST < T:
                 yield ("async", f"qf{(i + NST) % NST}")
             yield ("arrive", f"dqe{i % NDQ}")
+            if i + NST < T:
+                yield ("wait", f"qf{(i + NST) % NST}", (i + NST) // NST)
+                yield ("arrive", f"qr{(i + NST) % NST}")
 
     actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W0": W(0), "W1": W(1), "D": Dr()}
     pending = {k: None for k in actors}     # the blocking wait of each actor

@@ -272,7 +272,47 @@ def research_block_case(name, seed, B, D, H, n, dqk, dv, concat_ua):
                os.path.join(HERE, f"research_block_{name}.pt"))
 
 
+def position_case(name, seed, B, max_uih, max_targets, D, max_ctx, interleave, bucket_fn, dtype, with_targets=True):
+    # input recipe of ops/tests/position_test.py:96-170; eager path ops/position.py:43-96 -> ops/pytorch/pt_position.py:75-134
+    from generative_recommenders.ops.position import add_timestamp_positional_embeddings
+
+    g = torch.Generator().manual_seed(seed)
+    alpha = 0.5 if seed % 2 else 1.7
+    num_targets = torch.randint(max_targets + 1, (B,), generator=g)
+    lengths = torch.randint(max_uih + 1, (B,), generator=g) + num_targets * (2 if interleave else 1)
+    lengths[0] = max(int(lengths[0]), 1)
+    off = offsets_from(lengths.tolist())
+    max_seq_len = max_uih + max_targets * (2 if interleave else 1)
+    pos_w = torch.empty(max_seq_len, D).uniform_(-1.0, 1.0, generator=g).requires_grad_()
+    ts_w = torch.empty(200, D).uniform_(-1.0, 1.0, generator=g).requires_grad_()  # the reference test uses 1000 rows; 200 > D - 1 keeps the fixture small
+    x = torch.empty(int(off[-1]), D).uniform_(-0.1, 0.1, generator=g).to(dtype).requires_grad_()
+    deltas = torch.randint(86400, (B, max_seq_len), generator=g)
+    ts_dense = deltas.cumsum(dim=1)
+    mask = torch.arange(max_seq_len) < lengths.unsqueeze(1)
+    ts = ts_dense[mask]
+    out = add_timestamp_positional_embeddings(
+        alpha=alpha, max_seq_len=max_seq_len, max_contextual_seq_len=max_ctx, position_embeddings_weight=pos_w,
+        timestamp_embeddings_weight=ts_w, seq_offsets=off, seq_lengths=lengths, seq_embeddings=x, timestamps=ts,
+        num_targets=num_targets if with_targets else None, interleave_targets=interleave, time_bucket_fn=bucket_fn, kernel=PT)
+    dout = (torch.randn(out.shape, generator=g) * 0.01).to(out.dtype)
+    out.backward(dout)
+    torch.save(dict(name=name, alpha=alpha, max_seq_len=max_seq_len, max_contextual_seq_len=max_ctx, interleave_targets=interleave,
+                    time_bucket_fn=bucket_fn, pos_w=pos_w.detach(), ts_w=ts_w.detach(), seq_offsets=off, seq_lengths=lengths,
+                    x=x.detach(), timestamps=ts, num_targets=num_targets if with_targets else None, dout=dout, out=out.detach(),
+                    dx=x.grad, dpos_w=pos_w.grad, dts_w=ts_w.grad),
+               os.path.join(HERE, f"position_{name}.pt"))
+
+
 def main():
+    only = set(sys.argv[1:])  # e.g. `make_golden.py position`: regenerate only the named groups
+    if not only or "position" in only:
+        position_case("log_f32", 81, 5, 60, 10, 40, 0, False, "log", torch.float32)
+        position_case("sqrt_ctx_bf16", 82, 6, 90, 8, 64, 5, False, "sqrt", torch.bfloat16)
+        position_case("log_interleave_f16", 83, 4, 50, 6, 24, 3, True, "log", torch.float16)
+        position_case("sqrt_d136", 84, 4, 70, 5, 136, 0, False, "sqrt", torch.float32)
+    if only:
+        print("golden vectors written to", HERE, "for", sorted(only))
+        return
     f32, bf16 = torch.float32, torch.bfloat16
     #          name        seed B  H  uih tgt dqk dv  targets  mal ctx min_full dtype
     attn_case("plain", 1, 4, 2, 40, 6, 16, 16, False, 0, 0, 0, f32)

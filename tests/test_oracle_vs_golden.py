@@ -124,3 +124,16 @@ def test_research_block(name):
     assert O.rel_l2(x.grad, g["dx"]) < 2e-6
     for k, ref in g["grads"].items():
         assert O.rel_l2(leaves[k].grad, ref) < 5e-6, k
+
+
+@pytest.mark.parametrize("fname", sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "position_*.pt"))))
+def test_position_embeddings_oracle_matches_reference_bit_exactly(fname):
+    """ops/position.py:43-96 through the eager path: integer routing (position index, time bucket) and all three roundings of the
+    16-bit path are restated exactly, so out / dx are bit-identical and the fp32 scatter-adds agree to the last few ulps."""
+    g = golden(fname)
+    out, dx, dpos, dts = O.add_timestamp_positional_embeddings(
+        g["alpha"], g["max_contextual_seq_len"], g["pos_w"], g["ts_w"], g["seq_offsets"], g["seq_lengths"], g["x"], g["timestamps"],
+        g["num_targets"], g["interleave_targets"], g["time_bucket_fn"], g["dout"])
+    assert torch.equal(out, g["out"]) and torch.equal(dx, g["dx"])
+    torch.testing.assert_close(dpos, g["dpos_w"], rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(dts, g["dts_w"], rtol=1e-6, atol=1e-7)
