@@ -41,6 +41,16 @@ class AttnParams(C.Structure):
     ]
 
 
+class SslParams(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("dtype", C.c_int32), ("N", C.c_int64), ("R", C.c_int32), ("D", C.c_int32),
+        ("l2_norm", C.c_int32), ("l2_eps", C.c_float), ("temperature", C.c_float), ("reserved0", C.c_int32),
+        ("q", C.c_void_p), ("pos_emb", C.c_void_p), ("table", C.c_void_p), ("pos_ids", C.c_void_p), ("neg_ids", C.c_void_p),
+        ("logits", C.c_void_p), ("rnorm", C.c_void_p), ("lse", C.c_void_p), ("loss_rows", C.c_void_p),
+        ("row_coef", C.c_void_p), ("d_q", C.c_void_p), ("d_pos_emb", C.c_void_p), ("d_table", C.c_void_p),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 _i32, _i64, _f32, _u64, _vp = C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_void_p
@@ -68,6 +78,8 @@ _PROTOS = {
     "hstu_jagged_split": (C.c_int, [_vp] * 5 + [_i32] * 8 + [_vp]),
     "hstu_position_embeddings_fwd": (C.c_int, [_vp] * 10 + [_i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "hstu_position_embeddings_bwd": (C.c_int, [_vp] * 6 + [_i64, _i32, _f32, _i32, _vp]),
+    "hstu_sampled_softmax_fwd": (C.c_int, [C.POINTER(SslParams), _vp]),
+    "hstu_sampled_softmax_bwd": (C.c_int, [C.POINTER(SslParams), _vp]),
     "hstu_umma_selftest": (C.c_int, [C.c_char_p, C.c_size_t]),
 }
 

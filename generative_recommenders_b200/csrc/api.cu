@@ -276,6 +276,34 @@ int hstu_position_embeddings_bwd(const void* dout, void* d_seq_embeddings, float
   return position_bwd(dout, d_seq_embeddings, d_pos_w, d_ts_w, pos_inds, ts_inds, total_rows, D, alpha, dtype, (cudaStream_t)stream);
 }
 
+static int validate_ssl(const hstu_ssl_params* p, bool bwd) {
+  HSTU_CHECK_ARG(p != nullptr, "params is NULL");
+  HSTU_CHECK_ARG(p->abi_version == HSTU_B200_ABI_VERSION, "ABI version mismatch: caller %d, library %d", p->abi_version,
+                 HSTU_B200_ABI_VERSION);
+  HSTU_CHECK_ARG(p->N >= 0 && p->R >= 0 && p->D > 0, "sampled softmax: bad sizes");
+  HSTU_CHECK_ARG(p->temperature > 0.f, "sampled softmax: temperature must be positive");
+  if (p->N == 0) return 0;
+  HSTU_CHECK_ARG(p->q && p->pos_emb && p->table && p->pos_ids && (p->neg_ids || p->R == 0), "sampled softmax: NULL input");
+  HSTU_CHECK_ARG(p->logits && p->rnorm && p->lse, "sampled softmax: NULL logits / rnorm / lse");
+  if (!bwd) HSTU_CHECK_ARG(p->loss_rows != nullptr, "sampled softmax: NULL loss_rows");
+  if (bwd) HSTU_CHECK_ARG(p->row_coef && p->d_q && p->d_pos_emb && p->d_table, "sampled softmax backward: NULL argument");
+  return 0;
+}
+
+int hstu_sampled_softmax_fwd(const hstu_ssl_params* p, void* stream) {
+  if (int e = validate_ssl(p, false)) return e;
+  if (p->N == 0) return 0;
+  if (int e = bind_device(p->q)) return e;
+  return sampled_softmax_fwd(*p, p->dtype, (cudaStream_t)stream);
+}
+
+int hstu_sampled_softmax_bwd(const hstu_ssl_params* p, void* stream) {
+  if (int e = validate_ssl(p, true)) return e;
+  if (p->N == 0) return 0;
+  if (int e = bind_device(p->q)) return e;
+  return sampled_softmax_bwd(*p, p->dtype, (cudaStream_t)stream);
+}
+
 int hstu_umma_selftest(char* report, size_t report_bytes) { return umma_selftest(report, report_bytes); }
 
 }  // extern "C"

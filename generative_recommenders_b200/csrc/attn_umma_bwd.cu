@@ -168,12 +168,14 @@ __global__ void dout_amax_kernel(const uint16_t* __restrict__ dout, long long ro
 
 __device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-// 512 threads = 4 warpgroups with their own register budgets (setmaxnreg; 128 regs / thread at launch):
-//   warps 0-3   issuers X (scores), YV (dV), YK (dK), Z (dQ): one elected lane each                      -> 64 regs
-//   warps 4-11  two elementwise warpgroups (64 scores + 64 dP per thread in flight)                       -> 176 regs
-//   warps 12-15 dQ drain warpgroup; its elected lane is also the TMA producer (both follow tile_done)     -> 88 regs
+// 768 threads = 6 warpgroups with their own register budgets (setmaxnreg; 80 regs / thread at launch):
+//   warps 0-3    issuers X (scores), YV (dV), YK (dK), Z (dQ): one elected lane each                      -> 64 regs
+//   warps 4-19   FOUR elementwise warpgroups: warpgroup w handles 32 of the 64 query columns (chunk w & 1) of the units of
+//                half w >> 1.  Four warps per scheduler instead of two: the stage is bound by MUFU + dependent-issue latency,
+//                and with two warps per scheduler the MUFU pipe sat idle 40 % of the time (r02 timeline)      -> 88 regs
+//   warps 20-23  dQ drain warpgroup; its elected lane is also the TMA producer; converts bf16 tiles to fp16 -> 88 regs
 template <int D, bool BF16>
-__global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = BwdCfg<D>;
   constexpr int SW = Cfg::SW;
   constexpr int NST = Cfg::STAGES;
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       mbar_init(&bars->tile_done[i], 3);   // the commits of YV, YK and Z
     }
     for (int i = 0; i < 3; ++i) mbar_init(&bars->s_full[i], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&bars->unit_done[i], 128);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars->unit_done[i], 256);  // the two warpgroups that share a unit
     for (int i = 0; i < 2; ++i) mbar_init(&bars->dq_empty[i], 128);
     mbar_init(&bars->fin_full, 2);         // YV (dV) and YK (dK)
     mbar_init(&bars->kv_ready, 128);
@@ -312,8 +314,9 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         if (leader) {
           HSTU_TSTAMP(1, u, 1);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
-            mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (u > 0) || (ks > 0));
+          for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half; P^T of query chunk c sits at columns [32 c, 32 c + 16)
+            mma_ts(tmem + Cfg::TMEM_DV, tp + (ks >> 1) * 32 + (ks & 1) * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv,
+                   (u > 0) || (ks > 0));
           mma_commit(&bars->slot_free[slot]);                // the score issuer may overwrite the slot
           if (hf == 1) mma_commit(&bars->tile_done[i & 3]);  // this issuer is done with dO_i
           HSTU_TSTAMP(1, u, 2);
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         __syncwarp();
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp >= 20) {
     reg_dealloc<88>();
     // ---------------- dQ drain warpgroup (+ TMA producer on its elected lane) ----------------
     // dQ tile of query tile i: TMEM (lane = query row) -> swizzled fp32 staging box (32 columns) in shared memory -> ONE TMA
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     const int quad = warp & 3;
     const int row = quad * 32 + lane;              // query row inside the tile == TMEM lane
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
-    const bool elected = warp == 12 && lane == 0;
+    const bool elected = warp == 20 && lane == 0;
     auto load_tile = [&](int i) {
       const int st = i % NST;
       mbar_arrive_expect_tx(&bars->q_full[st], 2 * Cfg::TILE_BYTES);
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       }
       for (int i = 0; i < NST && i < T; ++i) load_tile(i);
     }
-    const int ct = tid - 384;  // index inside this warpgroup
+    const int ct = tid - 640;  // index inside this warpgroup
     auto convert_tile = [&](int i) {  // Q_i (as is) and dO_i (times 2^-e) of stage i % NST: bf16 -> fp16 in place
       const int st = i % NST;
       mbar_wait(&bars->q_full[st], (i / NST) & 1);
@@ -457,9 +460,11 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     }
     if (elected) bulk_wait_group_read0();          // shared memory must stay valid until the last reduce has read it
   } else {
-    reg_alloc<176>();
+    reg_alloc<88>();
     // ---------------- elementwise warpgroups ----------------
-    const int wg = (warp - 4) >> 2;                // owns query columns [64*wg, 64*wg + 64) of every tile
+    const int wg = (warp - 4) >> 2;                // 0..3
+    const int hf = wg >> 1;                        // half of the query tile = which units (u = 2 i + hf)
+    const int cc = wg & 1;                         // 32-column chunk of the unit's 64 query columns
     const int quad = warp & 3;
     const int row = quad * 32 + lane;              // key row inside the tile == TMEM lane
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
@@ -473,31 +478,33 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     const bool fast = msk.fast != 0;
     const bool j_ok = j_pos < len;
     const bool j_hist = j_ok && (!msk.has_tgt || j_pos < msk.max_id);  // fast mask: valid = (j_hist & i > j) | (i == j)
-    const int cbase = wg * 64;
+    const int cbase = hf * 64;
+    const bool stamp = cc == 0 && quad == 0 && lane == 0;
 
     for (int i = 0; i < T; ++i) {
-      const int u = 2 * i + wg, slot = u % Cfg::NSLOT;
+      const int u = 2 * i + hf, slot = u % Cfg::NSLOT;
       const int m0 = q_tile(i) * 128;
-      if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 0);
+      if (stamp) HSTU_TSTAMP(2 + hf, i, 0);
       mbar_wait(&bars->s_full[u % Cfg::NSF], (u / Cfg::NSF) & 1);
       tc_fence_after_sync();
-      if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 1);
-      // classification of this half-tile (uniform over the warpgroup)
+      if (stamp) HSTU_TSTAMP(2 + hf, i, 1);
+      // classification of this half-tile (uniform over the two warpgroups of the unit)
       const int mh0 = m0 + cbase;                   // first query row of the half
       const bool full = fast && (mh0 >= n0 + 128) && (mh0 + 64 <= len) && (!msk.has_tgt || n0 + 128 <= msk.max_id);
       const int mode = full ? 0 : (fast ? 1 : 2);
-      const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + wg * 16384);
-      const int jr = j_pos - m0 - cbase;           // query column (relative to this warpgroup's block) equal to j
+      const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + hf * 16384);
+      const int jr = j_pos - m0 - cbase;           // query column (relative to the half) equal to j
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
       const uint32_t st_addr = tmem + Cfg::TMEM_SLOT + slot * 128 + lane_bits;
       const uint32_t dp_addr = st_addr + 64;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {  // 2 chunks of 32 query columns
-        uint32_t s[32], dp[32];
-        tmem_ld32(st_addr + c * 32, s);
-        tmem_ld32(dp_addr + c * 32, dp);
+      for (int sc = 0; sc < 2; ++sc) {  // 2 sub-chunks of 16 query columns
+        const int col0 = cc * 32 + sc * 16;
+        uint32_t s[16], dp[16];
+        tmem_ld16(st_addr + col0, s);
+        tmem_ld16(dp_addr + col0, dp);
         tmem_ld_wait();
-        uint32_t pp[16], dd[16];
+        uint32_t pp[8], dd[8];
         // p = x sig(x) and g = sig (1 + x (1 - sig)) from one tanh: x = 2 hh, sig = (1 + t) / 2
         // packed fp32x2 arithmetic (FMUL2 / FFMA2): two elements per issued instruction, one MUFU.TANH per element
 #define HSTU_BWD_ELEM2(E, P0, P1, D0, D1)                                                                      \
@@ -513,7 +520,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
   }
         if (mode == 0) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
+          for (int e = 0; e < 16; e += 2) {
             float p0, p1, d0, d1;
             HSTU_BWD_ELEM2(e, p0, p1, d0, d1);
             pp[e >> 1] = pack_f16x2_sat(p0, p1);
@@ -524,10 +531,10 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
           const int lo_c = j_hist ? jr : 0x7fffffff;       // columns > lo_c are valid (if j is a history position)
           const int dg_c = j_ok ? jr : -0x7fffffff;        // the diagonal column
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
+          for (int e = 0; e < 16; e += 2) {
             float p0, p1, d0, d1;
             HSTU_BWD_ELEM2(e, p0, p1, d0, d1);
-            const int c0 = c * 32 + e;
+            const int c0 = col0 + e;
             const bool v0 = ((c0 > lo_c) | (c0 == dg_c)) & (c0 < len_rel);
             const bool v1 = ((c0 + 1 > lo_c) | (c0 + 1 == dg_c)) & (c0 + 1 < len_rel);
             p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;
@@ -537,10 +544,10 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
+          for (int e = 0; e < 16; e += 2) {
             float p0, p1, d0, d1;
             HSTU_BWD_ELEM2(e, p0, p1, d0, d1);
-            const int i_pos = m0 + cbase + c * 32 + e;
+            const int i_pos = m0 + cbase + col0 + e;
             const bool v0 = j_ok && i_pos < len && mask_valid(msk, i_pos, j_pos);
             const bool v1 = j_ok && i_pos + 1 < len && mask_valid(msk, i_pos + 1, j_pos);
             p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;
@@ -550,31 +557,34 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
           }
         }
 #undef HSTU_BWD_ELEM2
-        if (c == 0 && i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
-        // P^T chunk c (32 fp16 = 16 columns) overwrites the already-read front of the S^T half of the slot: A of the dV GEMM
-        tmem_st16(st_addr + c * 16, pp);
+        if (sc == 0 && i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
+        // P^T of these 16 query columns (16 fp16 = 8 TMEM columns) goes to columns [32 cc + 8 sc, + 8) of the slot: a part of
+        // THIS warpgroup's S^T region that it has already read (the neighbour warpgroup reads / writes only [32 (1-cc), +32))
+        tmem_st8(st_addr + cc * 32 + sc * 8, pp);
         // dS^T [kv][q] (16-byte stores): A of dK as stored, A of dQ read MN-major
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4)
-          st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + j4), dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
+        st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, cc * 4 + sc * 2), dd[0], dd[1], dd[2], dd[3]);
+        st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, cc * 4 + sc * 2 + 1), dd[4], dd[5], dd[6], dd[7]);
       }
       tmem_st_wait();
       tc_fence_before_sync();
       fence_proxy_async_smem();
-      if (quad == 0 && lane == 0) HSTU_TSTAMP(2 + wg, i, 2);
-      mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);
+      if (stamp) HSTU_TSTAMP(2 + hf, i, 2);
+      mbar_arrive(&bars->unit_done[hf * 2 + (i & 1)]);
     }
     // ---------------- epilogue: dV (warpgroup 0) / dK (warpgroup 1): TMEM -> scale -> global ----------------
     mbar_wait(&bars->fin_full, 0);
     tc_fence_after_sync();
-    const uint32_t acc = tmem + (wg == 0 ? Cfg::TMEM_DV : Cfg::TMEM_DK) + lane_bits;
+    // warpgroups 0 / 2: the two column halves of dV, warpgroups 1 / 3: of dK
+    const bool is_dv = cc == 0;
+    const int ecol0 = hf * (D / 2);
+    const uint32_t acc = tmem + (is_dv ? Cfg::TMEM_DV : Cfg::TMEM_DK) + ecol0 + lane_bits;
     // undo 2^-e (a power of two: exact): dK always carries it, dV only when dO itself was scaled
-    const float scale = wg == 0 ? (CONV ? p.dv_scale / ds_scale : p.dv_scale) : p.dk_scale / ds_scale;
-    uint16_t* gptr = wg == 0
+    const float scale = is_dv ? (CONV ? p.dv_scale / ds_scale : p.dv_scale) : p.dk_scale / ds_scale;
+    uint16_t* gptr = (is_dv
         ? reinterpret_cast<uint16_t*>(p.dv) + (row0 + j_pos) * p.dv_row_stride + (long long)h * p.dv_head_stride
-        : reinterpret_cast<uint16_t*>(p.dk) + (row0 + j_pos) * p.dk_row_stride + (long long)h * p.dk_head_stride;
+        : reinterpret_cast<uint16_t*>(p.dk) + (row0 + j_pos) * p.dk_row_stride + (long long)h * p.dk_head_stride) + ecol0;
 #pragma unroll
-    for (int c = 0; c < D / 16; ++c) {
+    for (int c = 0; c < D / 32; ++c) {
       uint32_t o[16];
       tmem_ld16(acc + c * 16, o);
       tmem_ld_wait();
@@ -704,7 +714,7 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   cudaMemset(tbuf, 0, tbytes);
   cudaMemcpyToSymbol(g_trace, &tbuf, sizeof(tbuf));
 #endif
-  kern<<<grid, 512, Cfg::SMEM_BYTES, st>>>(bp);
+  kern<<<grid, 768, Cfg::SMEM_BYTES, st>>>(bp);
   HSTU_CUDA_OK(cudaGetLastError());
 #ifdef HSTU_TRACE
   {

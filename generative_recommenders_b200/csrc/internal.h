@@ -60,6 +60,11 @@ int position_fwd(const PosArgs& a, int dtype, cudaStream_t st);
 int position_bwd(const void* dout, void* dseq, float* dpos, float* dts, const int* pos_inds, const int* ts_inds, long long L, int D,
                  float alpha, int dtype, cudaStream_t st);
 
+// sampled_softmax.cu
+typedef hstu_ssl_params SslArgs;
+int sampled_softmax_fwd(const SslArgs& a, int dtype, cudaStream_t st);
+int sampled_softmax_bwd(const SslArgs& a, int dtype, cudaStream_t st);
+
 // jagged.cu
 int jagged_concat_split(bool split, const void* a, const void* b, void* c, void* c2, const void* off_l, const void* off_r,
                         int is_i64, int batch, int dense_l, int dense_r, int n_prefix, int D, int elem_bytes,

@@ -26,6 +26,8 @@
  *        ops/triton/triton_jagged_tensors.py:31-142
  *   hstu_position_embeddings_fwd / _bwd
  *        ops/position.py:43-96, ops/pytorch/pt_position.py:39-134, ops/triton/triton_position.py:58-435
+ *   hstu_sampled_softmax_fwd / _bwd
+ *        research/modeling/sequential/losses/sampled_softmax.py:29-193, autoregressive_losses.py:73-121
  *   hstu_mask_valid / hstu_kv_tile_range (host-side helpers, no GPU needed)
  *        ops/pytorch/pt_hstu_attention.py:33-84 (_get_valid_attn_mask)
  */
@@ -200,6 +202,38 @@ int hstu_position_embeddings_fwd(const void* seq_embeddings, void* out, const fl
 int hstu_position_embeddings_bwd(const void* dout, void* d_seq_embeddings, float* d_pos_w, float* d_ts_w,
                                  const int32_t* pos_inds, const int32_t* ts_inds, int64_t total_rows, int32_t D, float alpha,
                                  int32_t dtype, void* cuda_stream);
+
+/* Fused sampled-softmax loss with dot-product similarity over negatives gathered straight from the item embedding table
+ * (research/modeling/sequential/losses/sampled_softmax.py:43-89; LocalNegativesSampler autoregressive_losses.py:73-121;
+ * dot_product_similarity_fn.py:31-67).  Row i: logits = [q_i . n(pos_emb_i), q_i . n(table[neg_ids[i, r]]) ...] / T with
+ * n(x) = x / max(||x||, l2_eps) if l2_norm; negatives whose id equals pos_ids[i] get -5e4; loss_rows[i] = lse_i - logits[i, 0].
+ * The weighted mean over rows is left to the caller.  D must be (16 / sizeof(dtype)) * 2^k, 2^k <= 32.                     */
+typedef struct hstu_ssl_params {
+  int32_t abi_version;  /* = HSTU_B200_ABI_VERSION */
+  int32_t dtype;        /* hstu_dtype of q, pos_emb, table, d_q, d_pos_emb */
+  int64_t N;            /* query rows */
+  int32_t R;            /* negatives per row */
+  int32_t D;            /* embedding dim */
+  int32_t l2_norm;
+  float l2_eps;
+  float temperature;
+  int32_t reserved0;
+  const void* q;            /* [N, D] */
+  const void* pos_emb;      /* [N, D] (before normalisation) */
+  const void* table;        /* [V, D] item embedding table */
+  const int64_t* pos_ids;   /* [N] */
+  const int64_t* neg_ids;   /* [N, R], every id < V */
+  float* logits;            /* [N, R + 1] fwd out / bwd in (column 0 = positive) */
+  float* rnorm;             /* [N, R + 1] fwd out / bwd in: 1 / max(||e||, eps) (1 without l2_norm) */
+  float* lse;               /* [N] fwd out / bwd in */
+  float* loss_rows;         /* [N] fwd out */
+  const float* row_coef;    /* [N] bwd in: dloss * w_i / sum(w) */
+  void* d_q;                /* [N, D] bwd out */
+  void* d_pos_emb;          /* [N, D] bwd out, zero-initialised by the caller */
+  float* d_table;           /* [V, D] fp32 bwd out, zero-initialised by the caller (atomically accumulated) */
+} hstu_ssl_params;
+int hstu_sampled_softmax_fwd(const hstu_ssl_params* p, void* cuda_stream);
+int hstu_sampled_softmax_bwd(const hstu_ssl_params* p, void* cuda_stream);
 
 /* On-device self test of the tcgen05 / TMA primitives the attention kernels are built from (K-major and MN-major
  * shared-memory descriptors, TMEM load/store).  Writes a report into `report` (host buffer).  Returns the number

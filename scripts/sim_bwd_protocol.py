@@ -7,7 +7,7 @@ phases behind (its parity test would then block until the barrier wraps).  Both 
 development (unit_done with a 3-slot ring; s_full with a single slot); this model reproduces them when the fix is removed
 (--break-ud / --break-sf).
 
-Actors: X (scores), YV (dV), YK (dK), Z (dQ) issuers, W0 / W1 elementwise warpgroups, D the dQ drain warpgroup whose elected
+Actors: X (scores), YV (dV), YK (dK), Z (dQ) issuers, four elementwise warpgroups W<half><chunk>, D the dQ drain warpgroup whose elected
 lane is also the TMA producer.  tcgen05.commit and TMA completions are asynchronous: they are queued per issuing actor and
 fire later, in order.
 usage: sim_bwd_protocol.py [--d 32|64|128] [--tiles T] [--seeds N] [--break-ud] [--break-sf]"""
@@ -43,7 +43,7 @@ def run(T, d, seed, break_ud=False, break_sf=False):
         B[f"qf{i}"] = Bar(1)
         B[f"qr{i}"] = Bar(1)       # bf16 inputs: tile converted to fp16 (128 drain threads modelled as one arrival)
         B[f"td{i}"] = Bar(3)       # YV, YK, Z
-        B[f"ud{i}"] = Bar(1)       # count 128 threads modelled as one arrival per warpgroup
+        B[f"ud{i}"] = Bar(2)       # the two warpgroups that share a unit (128 threads modelled as one arrival each)
     for i in range(3):
         B[f"sf{i}"] = Bar(1)
         B[f"free{i}"] = Bar(1)
@@ -120,7 +120,8 @@ def run(T, d, seed, break_ud=False, break_sf=False):
                 yield ("wait", f"qf{(i + NST) % NST}", (i + NST) // NST)
                 yield ("arrive", f"qr{(i + NST) % NST}")
 
-    actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W0": W(0), "W1": W(1), "D": Dr()}
+    # four elementwise warpgroups: (half 0, chunk 0/1), (half 1, chunk 0/1)
+    actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W00": W(0), "W01": W(0), "W10": W(1), "W11": W(1), "D": Dr()}
     pending = {k: None for k in actors}     # the blocking wait of each actor
     queues = {k: [] for k in actors}        # asynchronous completions (commit / TMA), in order per actor
     done = set()
