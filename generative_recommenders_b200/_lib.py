@@ -78,6 +78,8 @@ _PROTOS = {
     "hstu_jagged_split": (C.c_int, [_vp] * 5 + [_i32] * 8 + [_vp]),
     "hstu_position_embeddings_fwd": (C.c_int, [_vp] * 10 + [_i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "hstu_position_embeddings_bwd": (C.c_int, [_vp] * 6 + [_i64, _i32, _f32, _i32, _vp]),
+    "hstu_jagged_dense_bmm_broadcast_add": (C.c_int, [_vp] * 5 + [_i32] * 7 + [_vp]),
+    "hstu_jagged_dense_bmm_wgrad": (C.c_int, [_vp] * 5 + [_i32] * 6 + [_vp]),
     "hstu_sampled_softmax_fwd": (C.c_int, [C.POINTER(SslParams), _vp]),
     "hstu_sampled_softmax_bwd": (C.c_int, [C.POINTER(SslParams), _vp]),
     "hstu_umma_selftest": (C.c_int, [C.c_char_p, C.c_size_t]),

@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(ROOT, "build", "hstu_b200")
 LIB = os.path.join(HERE, "lib", "libhstu_b200.so")
 
-SOURCES = ["api.cu", "attn_generic.cu", "attn_umma_fwd.cu", "attn_umma_bwd.cu", "umma_selftest.cu", "tmap.cu", "norm.cu", "jagged.cu", "position.cu", "sampled_softmax.cu"]
+SOURCES = ["api.cu", "attn_generic.cu", "attn_umma_fwd.cu", "attn_umma_bwd.cu", "umma_selftest.cu", "tmap.cu", "norm.cu", "jagged.cu", "position.cu", "sampled_softmax.cu", "jagged_bmm.cu"]
 NVCC_FLAGS = [
     "-std=c++20", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcudafe", "--diag_suppress=177",

@@ -276,6 +276,28 @@ int hstu_position_embeddings_bwd(const void* dout, void* d_seq_embeddings, float
   return position_bwd(dout, d_seq_embeddings, d_pos_w, d_ts_w, pos_inds, ts_inds, total_rows, D, alpha, dtype, (cudaStream_t)stream);
 }
 
+int hstu_jagged_dense_bmm_broadcast_add(const void* jagged, const void* dense, const void* bias, void* out,
+                                        const void* seq_offsets, int32_t offsets_are_i64, int32_t batch, int32_t K, int32_t N,
+                                        int32_t max_seq_len, int32_t dense_is_transposed, int32_t dtype, void* stream) {
+  HSTU_CHECK_ARG(batch >= 0 && K > 0 && N > 0 && max_seq_len > 0, "jagged_dense_bmm_broadcast_add: bad sizes");
+  if (batch == 0) return 0;
+  if (int e = bind_device(dense)) return e;
+  HSTU_CHECK_ARG(dense && seq_offsets, "jagged_dense_bmm_broadcast_add: NULL argument");
+  return jagged_bmm(jagged, dense, bias, out, seq_offsets, offsets_are_i64, batch, K, N, max_seq_len, dense_is_transposed != 0, dtype,
+                    (cudaStream_t)stream);
+}
+
+int hstu_jagged_dense_bmm_wgrad(const void* jagged, const void* dout, void* d_dense, void* d_bias, const void* seq_offsets,
+                                int32_t offsets_are_i64, int32_t batch, int32_t K, int32_t N, int32_t max_seq_len, int32_t dtype,
+                                void* stream) {
+  HSTU_CHECK_ARG(batch >= 0 && K > 0 && N > 0 && max_seq_len > 0, "jagged_dense_bmm_wgrad: bad sizes");
+  if (batch == 0) return 0;
+  if (int e = bind_device(d_dense)) return e;
+  HSTU_CHECK_ARG(d_dense && seq_offsets, "jagged_dense_bmm_wgrad: NULL argument");
+  return jagged_bmm_wgrad(jagged, dout, d_dense, d_bias, seq_offsets, offsets_are_i64, batch, K, N, max_seq_len, dtype,
+                          (cudaStream_t)stream);
+}
+
 static int validate_ssl(const hstu_ssl_params* p, bool bwd) {
   HSTU_CHECK_ARG(p != nullptr, "params is NULL");
   HSTU_CHECK_ARG(p->abi_version == HSTU_B200_ABI_VERSION, "ABI version mismatch: caller %d, library %d", p->abi_version,

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
       }
     }
   } else if (warp >= 20) {
-    reg_dealloc<88>();
+    reg_alloc<88>();  // 80 at launch (768 threads): this is an increase (setmaxnreg.dec to a LARGER count is an illegal instruction)
     // ---------------- dQ drain warpgroup (+ TMA producer on its elected lane) ----------------
     // dQ tile of query tile i: TMEM (lane = query row) -> swizzled fp32 staging box (32 columns) in shared memory -> ONE TMA
     // reduce-add per box into dq_acc.  Two staging boxes alternate, so a reduce may still be reading one while the next is being

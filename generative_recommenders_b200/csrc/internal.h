@@ -65,6 +65,12 @@ typedef hstu_ssl_params SslArgs;
 int sampled_softmax_fwd(const SslArgs& a, int dtype, cudaStream_t st);
 int sampled_softmax_bwd(const SslArgs& a, int dtype, cudaStream_t st);
 
+// jagged_bmm.cu
+int jagged_bmm(const void* A, const void* Bm, const void* bias, void* C, const void* off, int off_i64, int batch, int K, int N,
+               int max_seq_len, bool trans_b, int dtype, cudaStream_t st);
+int jagged_bmm_wgrad(const void* A, const void* G, void* dW, void* dbias, const void* off, int off_i64, int batch, int K, int N,
+                     int max_seq_len, int dtype, cudaStream_t st);
+
 // jagged.cu
 int jagged_concat_split(bool split, const void* a, const void* b, void* c, void* c2, const void* off_l, const void* off_r,
                         int is_i64, int batch, int dense_l, int dense_r, int n_prefix, int D, int elem_bytes,

@@ -180,3 +180,71 @@ def hstu_concat_l2_embeddings(max_prefix_len: int, prefix_x: torch.Tensor, prefi
     require_cuda_kernel(kernel, "hstu_concat_l2_embeddings")
     return _Concat2DJaggedFunction.apply(max_prefix_len + max_l2_len, prefix_x, l2_x, max_prefix_len, max_l2_len,
                                          prefix_offsets, l2_offsets, contextual_seq_len)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# jagged x dense batched matmul + broadcast bias  (ops/jagged_tensors.py:210-253 of the reference)
+# ------------------------------------------------------------------------------------------------------------------
+def _bmm(jagged, dense, bias, seq_offsets, max_seq_len, n_out, transposed):
+    dev = jagged.device
+    B = dense.shape[0]
+    K = jagged.shape[1]
+    out = torch.empty((jagged.shape[0], n_out), dtype=jagged.dtype, device=dev)
+    with torch.cuda.device(dev), _lib.timed("jagged_bmm", dev):
+        _lib.check(_lib.lib().hstu_jagged_dense_bmm_broadcast_add(
+            jagged.data_ptr(), dense.data_ptr(), _lib.ptr(bias), out.data_ptr(), seq_offsets.data_ptr(),
+            int(seq_offsets.dtype == torch.int64), B, K, n_out, int(max_seq_len), int(transposed), _lib.dtype_code(jagged),
+            _lib.stream_ptr(dev)), "hstu_jagged_dense_bmm_broadcast_add")
+        _lib.note_launch(1)
+    return out
+
+
+class _JaggedDenseBmmBroadcastAddFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, max_seq_len, seq_offsets, jagged, dense, bias):
+        _lib.require_cuda(jagged, dense, bias, seq_offsets)
+        if not (jagged.dtype == dense.dtype == bias.dtype):
+            raise RuntimeError("jagged_dense_bmm_broadcast_add: jagged, dense and bias must share a dtype")
+        jagged, dense, bias = jagged.contiguous(), dense.contiguous(), bias.contiguous()
+        seq_offsets = _off(seq_offsets)
+        ctx.save_for_backward(seq_offsets, jagged, dense)
+        ctx.max_seq_len = int(max_seq_len)
+        return _bmm(jagged, dense, bias, seq_offsets, max_seq_len, dense.shape[2], False)
+
+    @staticmethod
+    def backward(ctx, dout):
+        seq_offsets, jagged, dense = ctx.saved_tensors
+        dev = dout.device
+        dout = dout.contiguous()
+        B, K, N = dense.shape
+        # d_jagged[rows of b] = dout[rows of b] @ dense[b]^T : the same kernel with the dense operand read transposed
+        d_jagged = _bmm(dout, dense, None, seq_offsets, ctx.max_seq_len, K, True)
+        d_dense = torch.empty_like(dense)
+        d_bias = torch.empty((B, N), dtype=dense.dtype, device=dev)
+        with torch.cuda.device(dev), _lib.timed("jagged_bmm_wgrad", dev):
+            _lib.check(_lib.lib().hstu_jagged_dense_bmm_wgrad(
+                jagged.data_ptr(), dout.data_ptr(), d_dense.data_ptr(), d_bias.data_ptr(), seq_offsets.data_ptr(),
+                int(seq_offsets.dtype == torch.int64), B, K, N, ctx.max_seq_len, _lib.dtype_code(jagged), _lib.stream_ptr(dev)),
+                "hstu_jagged_dense_bmm_wgrad")
+            _lib.note_launch(1)
+        return None, None, d_jagged, d_dense, d_bias
+
+
+def jagged_dense_bmm_broadcast_add(
+    max_seq_len: int,
+    seq_offsets: torch.Tensor,
+    jagged: torch.Tensor,
+    dense: torch.Tensor,
+    bias: torch.Tensor,
+    kernel: HammerKernel = HammerKernel.CUDA,
+) -> torch.Tensor:
+    """Drop-in for generative_recommenders.ops.jagged_tensors.jagged_dense_bmm_broadcast_add (jagged_tensors.py:210-253):
+    out = jagged x dense + bias with jagged (sum_B(M_i), K), dense (B, K, N), bias (B, N) -> (sum_B(M_i), N)."""
+    _, K = jagged.shape
+    B, _, N = dense.shape
+    torch._assert(dense.shape[1] == K, "wrong dense shape[1]")
+    torch._assert(seq_offsets.shape[0] == B + 1, "wrong seq_offsets shape[0]")
+    torch._assert(bias.shape[0] == B, "wrong bias shape[0]")
+    torch._assert(bias.shape[1] == N, "wrong bias shape[1]")
+    require_cuda_kernel(kernel, "jagged_dense_bmm_broadcast_add")
+    return _JaggedDenseBmmBroadcastAddFunction.apply(max_seq_len, seq_offsets, jagged, dense, bias)

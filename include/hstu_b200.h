@@ -26,6 +26,8 @@
  *        ops/triton/triton_jagged_tensors.py:31-142
  *   hstu_position_embeddings_fwd / _bwd
  *        ops/position.py:43-96, ops/pytorch/pt_position.py:39-134, ops/triton/triton_position.py:58-435
+ *   hstu_jagged_dense_bmm_broadcast_add / hstu_jagged_dense_bmm_wgrad
+ *        ops/jagged_tensors.py:210-253, ops/pytorch/pt_jagged.py:77-98, ops/triton/triton_jagged.py:56-347
  *   hstu_sampled_softmax_fwd / _bwd
  *        research/modeling/sequential/losses/sampled_softmax.py:29-193, autoregressive_losses.py:73-121
  *   hstu_mask_valid / hstu_kv_tile_range (host-side helpers, no GPU needed)
@@ -202,6 +204,17 @@ int hstu_position_embeddings_fwd(const void* seq_embeddings, void* out, const fl
 int hstu_position_embeddings_bwd(const void* dout, void* d_seq_embeddings, float* d_pos_w, float* d_ts_w,
                                  const int32_t* pos_inds, const int32_t* ts_inds, int64_t total_rows, int32_t D, float alpha,
                                  int32_t dtype, void* cuda_stream);
+
+/* out[rows of sequence b] = jagged[rows of b] @ dense[b] + bias[b]  (ops/jagged_tensors.py:210-253, ops/pytorch/pt_jagged.py:77-98):
+ * jagged [L, K], dense [B, K, N] (or [B, N, K] with dense_is_transposed: the d_jagged = dout @ dense^T pass), bias [B, N] or NULL,
+ * out [L, N]; fp32 accumulation, result in `dtype`.  Rows at positions >= max_seq_len of a sequence are written as zeros.     */
+int hstu_jagged_dense_bmm_broadcast_add(const void* jagged, const void* dense, const void* bias, void* out,
+                                        const void* seq_offsets, int32_t offsets_are_i64, int32_t batch, int32_t K, int32_t N,
+                                        int32_t max_seq_len, int32_t dense_is_transposed, int32_t dtype, void* cuda_stream);
+/* d_dense[b] = jagged[rows of b]^T @ dout[rows of b]  ([B, K, N]);  d_bias[b] = sum of dout rows of b ([B, N], nullable).      */
+int hstu_jagged_dense_bmm_wgrad(const void* jagged, const void* dout, void* d_dense, void* d_bias, const void* seq_offsets,
+                                int32_t offsets_are_i64, int32_t batch, int32_t K, int32_t N, int32_t max_seq_len, int32_t dtype,
+                                void* cuda_stream);
 
 /* Fused sampled-softmax loss with dot-product similarity over negatives gathered straight from the item embedding table
  * (research/modeling/sequential/losses/sampled_softmax.py:43-89; LocalNegativesSampler autoregressive_losses.py:73-121;

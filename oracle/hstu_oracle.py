@@ -449,6 +449,48 @@ def add_timestamp_positional_embeddings(alpha, max_contextual_seq_len, pos_w, ts
 
 
 # --------------------------------------------------------------------------------------
+# jagged x dense bmm + broadcast bias -- ops/jagged_tensors.py:210-253, ops/pytorch/pt_jagged.py:77-98
+# --------------------------------------------------------------------------------------
+
+
+def jagged_dense_bmm_broadcast_add(max_seq_len, seq_offsets, jagged, dense, bias):
+    """out[rows of b] = jagged[rows of b] @ dense[b] + bias[b], operands promoted to fp32 and the result cast back to the dtype
+    of `jagged` (pt_jagged.py:84-97); one sequence at a time (exact: sequences are independent).  Differentiable (autograd)."""
+    off = _lens(seq_offsets)
+    outs = []
+    for b in range(len(off) - 1):
+        s, e = int(off[b]), int(off[b + 1])
+        rows = jagged[s:e].to(torch.float32)
+        outs.append(rows @ dense[b].to(torch.float32) + bias[b].to(torch.float32).unsqueeze(0))
+    out = torch.cat(outs, dim=0) if outs else jagged.new_zeros((0, dense.shape[2]), dtype=torch.float32)
+    return out.to(jagged.dtype)
+
+
+# --------------------------------------------------------------------------------------
+# sampled-softmax loss -- research/modeling/sequential/losses/sampled_softmax.py:43-89 (dot-product similarity,
+# LocalNegativesSampler: autoregressive_losses.py:29-121)
+# --------------------------------------------------------------------------------------
+
+
+def sampled_softmax_loss(q, pos_ids, pos_emb, weights, neg_ids, table, temperature, l2_norm, l2_eps, dtype=torch.float32):
+    """Differentiable (torch autograd) restatement in `dtype`: returns the scalar loss."""
+    def norm(x):  # autoregressive_losses.py:39-45
+        if l2_norm:
+            x = x / torch.clamp(torch.linalg.norm(x, ord=2, dim=-1, keepdim=True), min=l2_eps)
+        return x
+
+    qf = q.to(dtype)
+    pe = norm(pos_emb.to(dtype))
+    ne = norm(table.to(dtype)[neg_ids])                                  # [N, R, D]
+    pos_logits = (qf * pe).sum(-1, keepdim=True) / temperature           # dot_product_similarity_fn.py:62-67 with X = 1
+    neg_logits = torch.bmm(ne, qf.unsqueeze(2)).squeeze(2) / temperature
+    neg_logits = torch.where(pos_ids.unsqueeze(1) == neg_ids, torch.full_like(neg_logits, -5e4), neg_logits)  # :80-84
+    rows = -torch.nn.functional.log_softmax(torch.cat([pos_logits, neg_logits], dim=1), dim=1)[:, 0]
+    w = weights.to(dtype)
+    return (rows * w).sum() / w.sum()
+
+
+# --------------------------------------------------------------------------------------
 # jagged row routing (integer-exact)  -- ops/pytorch/pt_jagged_tensors.py
 # --------------------------------------------------------------------------------------
 

@@ -303,8 +303,79 @@ def position_case(name, seed, B, max_uih, max_targets, D, max_ctx, interleave, b
                os.path.join(HERE, f"position_{name}.pt"))
 
 
+def ssl_case(name, seed, B, N, D, R, V, l2_norm, temperature, dtype):
+    # research/modeling/sequential/losses/sampled_softmax.py:91-193 (dense forward -> jagged_forward) with the sampler and the
+    # similarity the HSTU configs use (LocalNegativesSampler, DotProductSimilarity)
+    from generative_recommenders.research.modeling.sequential.autoregressive_losses import LocalNegativesSampler
+    from generative_recommenders.research.modeling.sequential.losses.sampled_softmax import SampledSoftmaxLoss
+    from generative_recommenders.research.rails.similarities.dot_product_similarity_fn import DotProductSimilarity
+
+    class _Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self._sim = DotProductSimilarity()
+
+        def similarity_fn(self, query_embeddings, item_ids, item_embeddings, **kwargs):
+            return self._sim(query_embeddings=query_embeddings, item_embeddings=item_embeddings)
+
+    torch.manual_seed(seed)
+    emb = torch.nn.Embedding(V, D)
+    with torch.no_grad():
+        emb.weight.normal_(0, 0.3)
+        emb.weight[3].mul_(1e-9)  # one row whose norm is clamped by l2_norm_eps
+    emb = emb.to(dtype)
+    sampler = LocalNegativesSampler(num_items=V, item_emb=emb, all_item_ids=list(range(V)), l2_norm=l2_norm, l2_norm_eps=1e-6)
+    loss_mod = SampledSoftmaxLoss(num_to_sample=R, softmax_temperature=temperature, model=_Model())
+    lengths = torch.randint(1, N + 1, (B,))
+    out = (torch.randn(B, N, D) * 0.5).to(dtype).requires_grad_()
+    ids = torch.randint(0, V, (B, N))
+    ids[0, 0] = 3
+    sup = emb(ids).detach().clone().requires_grad_()
+    w = (torch.rand(B, N) > 0.2).float() * torch.rand(B, N)
+    gen_state = torch.get_rng_state()
+    loss, _ = loss_mod(lengths=lengths, output_embeddings=out, supervision_ids=ids, supervision_embeddings=sup,
+                       supervision_weights=w.to(dtype), negatives_sampler=sampler)
+    loss.backward()
+    # the ids the sampler drew (same generator state, same call)
+    torch.set_rng_state(gen_state)
+    keep = torch.arange(N).unsqueeze(0) < lengths.unsqueeze(1)
+    sampled = torch.randint(low=0, high=V, size=(int(keep.sum()), R), dtype=ids.dtype)
+    torch.save(dict(name=name, R=R, V=V, l2_norm=l2_norm, l2_norm_eps=1e-6, temperature=temperature, lengths=lengths,
+                    output_embeddings=out.detach(), supervision_ids=ids, supervision_embeddings=sup.detach(), weights=w.to(dtype),
+                    table=emb.weight.detach().clone(), rng_state=gen_state, sampled_ids=sampled, loss=loss.detach(),
+                    d_out=out.grad, d_sup=sup.grad, d_table=emb.weight.grad),
+               os.path.join(HERE, f"ssl_{name}.pt"))
+
+
+def jagged_bmm_case(name, seed, B, max_len, K, N, dtype):
+    # ops/tests/jagged_tensors_test.py:_test_jagged_dense_bmm_broadcast_add recipe; eager path ops/pytorch/pt_jagged.py:77-98
+    from generative_recommenders.ops.jagged_tensors import jagged_dense_bmm_broadcast_add
+
+    g = torch.Generator().manual_seed(seed)
+    lengths = torch.randint(max_len + 1, (B,), generator=g)
+    lengths[0] = 0
+    off = offsets_from(lengths.tolist())
+    L = int(off[-1])
+    jag = torch.empty(L, K).uniform_(-1, 1, generator=g).to(dtype).requires_grad_()
+    dense = torch.empty(B, K, N).uniform_(-1, 1, generator=g).to(dtype).requires_grad_()
+    bias = torch.empty(B, N).uniform_(-1, 1, generator=g).to(dtype).requires_grad_()
+    out = jagged_dense_bmm_broadcast_add(max_seq_len=max_len, seq_offsets=off, jagged=jag, dense=dense, bias=bias, kernel=PT)
+    dout = torch.randn(out.shape, generator=g).to(dtype) * 0.1
+    out.backward(dout)
+    torch.save(dict(name=name, max_seq_len=max_len, seq_offsets=off, jagged=jag.detach(), dense=dense.detach(), bias=bias.detach(),
+                    dout=dout, out=out.detach(), d_jagged=jag.grad, d_dense=dense.grad, d_bias=bias.grad),
+               os.path.join(HERE, f"jagged_bmm_{name}.pt"))
+
+
 def main():
-    only = set(sys.argv[1:])  # e.g. `make_golden.py position`: regenerate only the named groups
+    only = set(sys.argv[1:])
+    if not only or "jagged_bmm" in only:
+        jagged_bmm_case("f32", 95, 5, 40, 24, 36, torch.float32)
+        jagged_bmm_case("bf16", 96, 4, 70, 64, 80, torch.bfloat16)
+    if not only or "ssl" in only:
+        ssl_case("l2_f32", 91, 4, 12, 64, 16, 50, True, 0.05, torch.float32)
+        ssl_case("plain_f32", 92, 3, 9, 32, 8, 40, False, 1.0, torch.float32)
+        ssl_case("l2_bf16", 93, 4, 10, 64, 32, 64, True, 0.05, torch.bfloat16)  # e.g. `make_golden.py position`: regenerate only the named groups
     if not only or "position" in only:
         position_case("log_f32", 81, 5, 60, 10, 40, 0, False, "log", torch.float32)
         position_case("sqrt_ctx_bf16", 82, 6, 90, 8, 64, 5, False, "sqrt", torch.bfloat16)
