@@ -168,12 +168,13 @@ __global__ void dout_amax_kernel(const uint16_t* __restrict__ dout, long long ro
 
 __device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-// 768 threads = 6 warpgroups with their own register budgets (setmaxnreg; 80 regs / thread at launch):
-//   warps 0-3    issuers X (scores), YV (dV), YK (dK), Z (dQ): one elected lane each                      -> 64 regs
+// 768 threads = 6 warpgroups with their own register budgets (setmaxnreg; 80 regs / thread at launch, and the CTA can only
+// redistribute THAT pool: increases beyond it would spin forever in setmaxnreg.inc):
+//   warps 0-3    issuers X (scores), YV (dV), YK (dK), Z (dQ): one elected lane each                      -> 56 regs
 //   warps 4-19   FOUR elementwise warpgroups: warpgroup w handles 32 of the 64 query columns (chunk w & 1) of the units of
 //                half w >> 1.  Four warps per scheduler instead of two: the stage is bound by MUFU + dependent-issue latency,
-//                and with two warps per scheduler the MUFU pipe sat idle 40 % of the time (r02 timeline)      -> 88 regs
-//   warps 20-23  dQ drain warpgroup; its elected lane is also the TMA producer; converts bf16 tiles to fp16 -> 88 regs
+//                and with two warps per scheduler the MUFU pipe sat idle 40 % of the time (r02 timeline)      -> 80 regs
+//   warps 20-23  dQ drain warpgroup; its elected lane is also the TMA producer; converts bf16 tiles to fp16 -> 96 regs
 template <int D, bool BF16>
 __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = BwdCfg<D>;
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
   const float ds_scale = ds_scale_from_amax(__ldg(p.dout_amax_bits));  // 2^-e
 
   if (warp < 4) {
-    reg_dealloc<64>();
+    reg_dealloc<56>();
     // ---------------- MMA issuers ----------------
     // Work is pipelined in "units" u = 2 i + h: half h (64 query rows) of query tile i.  Unit u's scores live in TMEM
     // slot u % NSLOT; warpgroup h turns them into P^T (fp16, over the front of the slot) and the dS^T box (pair i & 1,
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
       }
     }
   } else if (warp >= 20) {
-    reg_alloc<88>();  // 80 at launch (768 threads): this is an increase (setmaxnreg.dec to a LARGER count is an illegal instruction)
+    reg_alloc<96>();  // paid for by the issuer warps: the pool of a CTA is what it was launched with (768 x 80 registers)
     // ---------------- dQ drain warpgroup (+ TMA producer on its elected lane) ----------------
     // dQ tile of query tile i: TMEM (lane = query row) -> swizzled fp32 staging box (32 columns) in shared memory -> ONE TMA
     // reduce-add per box into dq_acc.  Two staging boxes alternate, so a reduce may still be reading one while the next is being
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
     }
     if (elected) bulk_wait_group_read0();          // shared memory must stay valid until the last reduce has read it
   } else {
-    reg_alloc<88>();
+    // (stays at the 80 registers of the launch: 4 x 128 x 80 + 128 x 56 + 128 x 96 = 768 x 80, the whole pool of the CTA)
     // ---------------- elementwise warpgroups ----------------
     const int wg = (warp - 4) >> 2;                // 0..3
     const int hf = wg >> 1;                        // half of the query tile = which units (u = 2 i + hf)
@@ -641,6 +642,7 @@ static bool aligned_view(const void* ptr, long long row_stride, long long head_s
 
 static bool umma_bwd_supported(const hstu_attn_params& p) {
   if (!umma_fwd_supported(p)) return false;  // dtype / dims / alignment of q, k, v (out is not used by the backward)
+  // d = 256: dK and dV alone fill the 512 TMEM columns; the forward has a tcgen05 kernel, the backward runs on the generic path
   if (p.dqk != 32 && p.dqk != 64 && p.dqk != 128) return false;
   return aligned_view(p.dout, p.do_row_stride, p.do_head_stride) && aligned_view(p.dq, p.dq_row_stride, p.dq_head_stride) &&
          aligned_view(p.dk, p.dk_row_stride, p.dk_head_stride) && aligned_view(p.dv_out, p.dv_row_stride, p.dv_head_stride);

@@ -50,7 +50,11 @@ struct FwdCfg {
   static constexpr int NBOX = D / BOX_COLS;
   static constexpr int BOX_BYTES = 128 * SW;
   static constexpr int TILE_BYTES = 128 * D * 2;
-  static constexpr int STAGES = 3;   // K / V TMA rings: stage = score slot = tile % 3 (their release shares the slot barriers)
+  // K / V TMA rings and the ring of score slots in TMEM.  d <= 128: three of each (stage = slot = tile % 3).  d = 256: a tile is
+  // 64 KB, so ONE K and ONE V stage next to Q, and the 256-column O accumulator leaves room for TWO 128-column score slots.  A K
+  // stage is released by the score GEMM that read it (s_full), a V stage and a score slot by the P.V GEMM (pv_done).
+  static constexpr int STAGES = (D <= 128) ? 3 : 1;
+  static constexpr int NSLOT = (D <= 128) ? 3 : 2;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + TILE_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * TILE_BYTES;
@@ -62,8 +66,9 @@ struct FwdCfg {
   // summed in the epilogue): consecutive tcgen05.mma into ONE accumulator are dependent and expose the MMA latency when
   // the instruction itself is short (N = d = 32: 16 clk of work).
   static constexpr int NACC = (D <= 32) ? 4 : (D <= 64 ? 2 : 1);
-  static constexpr int TMEM_O = 384;    // accumulators: columns [384, 384 + NACC * D)
-  static_assert(384 + NACC * D <= 512, "TMEM budget");
+  static constexpr int TMEM_O = NSLOT * 128;  // accumulators: columns [TMEM_O, TMEM_O + NACC * D)
+  static_assert(TMEM_O + NACC * D <= 512, "TMEM budget");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 struct FwdBars {
@@ -81,6 +86,7 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
   constexpr bool CONV = BF16;  // bf16 tiles are converted to fp16 in shared memory; every MMA below is fp16 x fp16
   constexpr int SW = Cfg::SW;
   constexpr int NST = Cfg::STAGES;
+  constexpr int NSL = Cfg::NSLOT;
   const int b = blockIdx.z, h = blockIdx.y;
   const int m0 = (int)(gridDim.x - 1 - blockIdx.x) * 128;
   const long long row0 = load_index(p.seq_offsets, p.offsets_i64, b);
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
         tma_load_3d(sQ + bx * Cfg::BOX_BYTES, &p.tmQ, &bars->q_full, bx * Cfg::BOX_COLS, h, (int)(row0 + m0));
       for (int i = 0; i < T; ++i) {
         const int st = i % NST;
-        if (i >= 3) mbar_wait(&bars->s_full[st], ((i / 3) - 1) & 1);  // Q K_{i-3}^T has consumed this stage
+        if (i >= NST) mbar_wait(&bars->s_full[(i - NST) % NSL], ((i - NST) / NSL) & 1);  // Q K_{i-NST}^T has consumed this stage
 #ifdef HSTU_EXP_NO_KLOAD
         if (i >= NST) {  // ablation experiment only
           mbar_arrive(&bars->k_full[st]);
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
       prefetch_tensormap(&p.tmV);
       for (int i = 0; i < T; ++i) {
         const int st = i % NST;
-        if (i >= 3) mbar_wait(&bars->pv_done[st], ((i / 3) - 1) & 1);  // P_{i-3} V_{i-3} has consumed this stage
+        if (i >= NST) mbar_wait(&bars->pv_done[(i - NST) % NSL], ((i - NST) / NSL) & 1);  // P_{i-NST} V_{i-NST} has consumed this stage
 #ifdef HSTU_EXP_NO_VLOAD
         if (i >= NST) {  // ablation experiment only: no TMA traffic for V after the ring has been filled once
           mbar_arrive(&bars->v_full[st]);
@@ -210,12 +216,12 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
     const uint64_t dk0 = desc_kmajor<SW>(smem_u32(sK), 0);
     mbar_wait(q_rdy, 0);
     for (int i = 0; i < T; ++i) {
-      const int st = i % 3;
-      if (i >= 3) mbar_wait(&bars->pv_done[st], ((i / 3) - 1) & 1);  // P_{i-3} (front of this slot) has been consumed
-      mbar_wait(&k_rdy[st], (i / 3) & 1);
+      const int st = i % NST, sl = i % NSL;
+      if (i >= NSL) mbar_wait(&bars->pv_done[sl], ((i / NSL) - 1) & 1);  // P_{i-NSL} (front of this slot) has been consumed
+      mbar_wait(&k_rdy[st], (i / NST) & 1);
       tc_fence_after_sync();
       const uint64_t kd = dk0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
-      const uint32_t ts = tmem + Cfg::TMEM_S + st * 128;
+      const uint32_t ts = tmem + Cfg::TMEM_S + sl * 128;
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
           const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
           mma_ss(ts, dq0 + o, kd + o, idesc_qk, ks > 0);
         }
-        mma_commit(&bars->s_full[st]);
+        mma_commit(&bars->s_full[sl]);
       }
       __syncwarp();
     }
@@ -233,18 +239,18 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
     constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, false, false);     // P (TMEM) and V both fp16
     const uint64_t dv0 = desc_mnmajor<SW>(smem_u32(sV), 0, Cfg::BOX_BYTES);
     for (int i = 0; i < T; ++i) {
-      const int st = i % 3;
-      mbar_wait(&bars->p_full[st], (i / 3) & 1);   // P_i sits in TMEM (front of score slot i % 3)
-      mbar_wait(&v_rdy[st], (i / 3) & 1);
+      const int st = i % NST, sl = i % NSL;
+      mbar_wait(&bars->p_full[sl], (i / NSL) & 1);   // P_i sits in TMEM (front of its score slot)
+      mbar_wait(&v_rdy[st], (i / NST) & 1);
       tc_fence_after_sync();
       const uint64_t vd = dv0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
-      const uint32_t tp = tmem + Cfg::TMEM_S + st * 128;
+      const uint32_t tp = tmem + Cfg::TMEM_S + sl * 128;
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)  // 16 bf16 of K per 8 TMEM columns
           mma_ts(tmem + Cfg::TMEM_O + (ks % Cfg::NACC) * D, tp + ks * 8, vd + (uint64_t)((ks * 16 * SW) >> 4), idesc_pv,
                  (i > 0) || (ks >= Cfg::NACC));
-        mma_commit(&bars->pv_done[st]);
+        mma_commit(&bars->pv_done[sl]);
       }
       __syncwarp();
     }
@@ -265,8 +271,8 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
     const int lim_i = msk.has_tgt ? min(i_pos, msk.max_id) : i_pos;
     const int full_lim = fast ? min(m0, msk.has_tgt ? msk.max_id : 0x7fffffff) : -1;
     for (int i = wg, it = 0; i < T; i += 2, ++it) {
-      const uint32_t s_taddr = tmem + Cfg::TMEM_S + (i % 3) * 128 + lane_bits;
-      mbar_wait(&bars->s_full[i % 3], (i / 3) & 1);
+      const uint32_t s_taddr = tmem + Cfg::TMEM_S + (i % NSL) * 128 + lane_bits;
+      mbar_wait(&bars->s_full[i % NSL], (i / NSL) & 1);
       tc_fence_after_sync();
       const int n0 = (t0 + i) * 128;
       const int mode = (n0 + 128 <= full_lim) ? 0 : (fast ? 1 : 2);  // tile-uniform: no divergence
@@ -323,7 +329,7 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
       }
       tmem_st_wait();
       tc_fence_before_sync();
-      mbar_arrive(&bars->p_full[i % 3]);
+      mbar_arrive(&bars->p_full[i % NSL]);
     }
     // ---------------- epilogue: O (TMEM) -> * 1/N -> global ----------------
     mbar_wait(&bars->o_full, 0);
@@ -381,7 +387,7 @@ static bool aligned_view(const void* ptr, long long row_stride, long long head_s
 
 bool umma_fwd_supported(const hstu_attn_params& p) {
   if (p.dtype != HSTU_BF16 && p.dtype != HSTU_F16) return false;
-  if (p.dqk != p.dv || (p.dqk != 32 && p.dqk != 64 && p.dqk != 128)) return false;
+  if (p.dqk != p.dv || (p.dqk != 32 && p.dqk != 64 && p.dqk != 128 && p.dqk != 256)) return false;
   if (p.delta_q_len != 0 || p.pos_w != nullptr || p.ts_w != nullptr) return false;
   if (p.total_rows >= (1ll << 31) - 256) return false;
   if (!aligned_view(p.q, p.q_row_stride, p.q_head_stride) || !aligned_view(p.k, p.k_row_stride, p.k_head_stride) ||
@@ -425,6 +431,7 @@ int attn_umma_fwd(const hstu_attn_params& p, cudaStream_t st) {
     case 32: return bf ? launch_fwd_umma<32, true>(p, st) : launch_fwd_umma<32, false>(p, st);
     case 64: return bf ? launch_fwd_umma<64, true>(p, st) : launch_fwd_umma<64, false>(p, st);
     case 128: return bf ? launch_fwd_umma<128, true>(p, st) : launch_fwd_umma<128, false>(p, st);
+    case 256: return bf ? launch_fwd_umma<256, true>(p, st) : launch_fwd_umma<256, false>(p, st);
   }
   set_error("tcgen05 forward: unsupported head dim %d", p.dqk);
   return HSTU_ERR_UNSUPPORTED;

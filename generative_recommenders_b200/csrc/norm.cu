@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(kNormThreads) nmd_fwd_kernel(const T* __restri
       const float xhat = (a[i] - mean) * rstd;
       const float nrm = group_norm ? xhat * gw + gb : xhat * wv[i] + bv[i];
       y[i] = uu[i] * nrm;
+      if (concat == 2) a[i] = nrm;  // concat_ua (research block): the middle part is Norm(attn), not attn
     }
     T* orow = out + r * os + gidx * len;
     if (p > 0.f) {
@@ -385,6 +386,9 @@ __global__ void __launch_bounds__(kNormThreads) nmd_bwd_kernel(
     float c1 = 0.f, c2 = 0.f, sgw = 0.f, sgb = 0.f;
 #pragma unroll
     for (int i = 0; i < PL; ++i) {
+      // concat_ua: the gradient of the middle part belongs to Norm(attn) and flows through the normalisation
+      const float g_mid = concat == 2 ? ga[i] : 0.f;
+      if (concat == 2) ga[i] = 0.f;
       const float upre = uu[i];
       float sg = 0.f;
       float ua = upre;
@@ -396,7 +400,7 @@ __global__ void __launch_bounds__(kNormThreads) nmd_bwd_kernel(
       const float wi = group_norm ? gw : wv[i];
       const float nrm = xhat * wi + (group_norm ? gb : bv[i]);
       float dua = gy[i] * nrm + gu[i];        // d/d u'
-      const float dn = gy[i] * ua;           // d/d Norm(attn)
+      const float dn = gy[i] * ua + g_mid;   // d/d Norm(attn)
       if (silu_u) dua *= sg * (1.f + upre * (1.f - sg));
       gu[i] = dua;
       if (group_norm) {

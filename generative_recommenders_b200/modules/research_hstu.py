@@ -131,17 +131,12 @@ class SequentialTransductionUnitJagged(HammerModule):
             rb._pos_w, rb._ts_w if all_timestamps is not None else None, all_timestamps,
         ).reshape(L, H * dv)
         residual = x + self._o.bias.to(x.dtype)
-        if self._concat_ua:
-            a = layer_norm(attn, self._ones_attn, self._zeros_attn, self._eps, kernel=kern)
-            u = u.contiguous()
-            o_input = torch.cat([u, a, u * a], dim=-1)
-            o_input = torch.nn.functional.dropout(o_input, p=self._dropout_ratio, training=self.training)
-            out = torch.addmm(residual, o_input, self._o.weight.to(x.dtype).t())
-        else:
-            # u * LN(attn) -> dropout -> x + y W_o: exactly the fused output stage of the STU block
-            out = hstu_compute_output(
-                attn=attn, u=u.contiguous(), x=residual, norm_weight=self._ones_attn, norm_bias=self._zeros_attn, norm_eps=self._eps,
-                output_weight=self._o.weight.t(), num_heads=H, linear_dim=dv, dropout_ratio=self._dropout_ratio,
-                training=self.training, concat_ux=False, group_norm=False, recompute_y_in_backward=False, kernel=kern,
-            )
+        # u * LN(attn) [or cat(u, a, u * a), a = LN(attn): concat mode 2 of the fused kernel] -> dropout -> x + y W_o: the fused
+        # output stage of the STU block (one kernel forward, one backward; nothing materialised in between)
+        out = hstu_compute_output(
+            attn=attn, u=u.contiguous(), x=residual, norm_weight=self._ones_attn, norm_bias=self._zeros_attn, norm_eps=self._eps,
+            output_weight=self._o.weight.t(), num_heads=H, linear_dim=dv, dropout_ratio=self._dropout_ratio,
+            training=self.training, concat_ux=2 if self._concat_ua else False, group_norm=False, recompute_y_in_backward=False,
+            kernel=kern,
+        )
         return out, (v, None, None, out)

@@ -156,7 +156,8 @@ int hstu_rms_norm_bwd(const void* dy, const void* x, const void* w, const float*
 
 /* Output stage (pt_hstu_linear.py:23-66): y = u' * Norm(attn) with u' = silu_u ? silu(u) : u; Norm = LayerNorm over
  * all H*dv columns (group_norm=0, w,b [H*dv]) or per-head GroupNorm (group_norm=1, w,b [H]).
- * concat_ux: out row = [u' | attn | y] (3*H*dv wide) else [y].  Dropout with keep-prob 1-p uses a counter-based
+ * concat_ux: 1: out row = [u' | attn | y] (3*H*dv wide); 2: [u' | Norm(attn) | y] (the research block's concat_ua,
+ * research/modeling/sequential/hstu.py:427-430); 0: [y].  Dropout with keep-prob 1-p uses a counter-based
  * generator keyed by (seed, element index); p = 0 is exact.  mean/rstd: [n_rows * (group_norm ? H : 1)].  */
 int hstu_norm_mul_dropout_fwd(const void* attn, const void* u, const void* w, const void* b, void* out, float* mean,
                               float* rstd, int64_t n_rows, int32_t heads, int32_t dv, int64_t attn_row_stride,

@@ -43,7 +43,19 @@ def test_umma_fwd_bwd_vs_oracle_at_bench_shapes(d, lmax, lengths, targets, H, dt
     q, k, v, dout, off, nt = _case(d, lmax, lengths, targets, H, dtype, 4242 + d)
     alpha = 1.0 / d**0.5
     qd, kd, vd = (t.to(DEV).requires_grad_() for t in (q, k, v))
-    out = hstu_mha(lmax, alpha, qd, kd, vd, off.to(DEV), num_targets=nt.to(DEV), kernel=HammerKernel.CUDA, impl=_lib.IMPL_UMMA)
+    # d = 256: tcgen05 forward, generic backward (dK + dV alone fill the tensor memory) -> AUTO; otherwise tcgen05 is forced
+    impl = _lib.IMPL_AUTO if d == 256 else _lib.IMPL_UMMA
+    if d == 256:
+        import ctypes as C
+
+        from generative_recommenders_b200.ops.hstu_attention import _fill_common
+
+        p = _lib.AttnParams()
+        _fill_common(p, lmax, alpha, qd, kd, vd, off.to(DEV), nt.to(DEV), 0, 0, 0, _lib.IMPL_AUTO)
+        o_ = torch.empty(qd.shape, device=DEV, dtype=dtype)
+        p.out, p.o_row_stride, p.o_head_stride = o_.data_ptr(), o_.stride(0), o_.stride(1)
+        assert _lib.lib().hstu_attn_select_impl(C.byref(p), 0) == _lib.IMPL_UMMA, "d = 256 forward must run on tcgen05"
+    out = hstu_mha(lmax, alpha, qd, kd, vd, off.to(DEV), num_targets=nt.to(DEV), kernel=HammerKernel.CUDA, impl=impl)
     out.backward(dout.to(DEV))
     ref = O.hstu_mha_fwd(lmax, alpha, q, k, v, off, nt)
     rdq, rdk, rdv = O.hstu_mha_bwd(lmax, alpha, dout, q, k, v, off, nt)
