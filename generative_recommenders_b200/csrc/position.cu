@@ -81,18 +81,19 @@ __global__ void __launch_bounds__(256) position_fwd_kernel(const PosArgs a) {
       T* oe = reinterpret_cast<T*>(&ov);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const T scaled = Cvt<T>::from_f(Cvt<T>::to_f(xe[k]) * a.alpha);
+        const T scaled = Cvt<T>::from_f(__fmul_rn(Cvt<T>::to_f(xe[k]), a.alpha));
         const T emb = Cvt<T>::from_f(pe[k]);
-        oe[k] = Cvt<T>::from_f(Cvt<T>::to_f(scaled) + Cvt<T>::to_f(emb));
+        oe[k] = Cvt<T>::from_f(__fadd_rn(Cvt<T>::to_f(scaled), Cvt<T>::to_f(emb)));
       }
       *reinterpret_cast<uint4*>(dst + col) = ov;
     }
     return;
   }
   for (int col = lane; col < a.D; col += 32) {
-    const T scaled = Cvt<T>::from_f(Cvt<T>::to_f(src[col]) * a.alpha);
-    const T emb = Cvt<T>::from_f(tw[col] + pw[col]);
-    dst[col] = Cvt<T>::from_f(Cvt<T>::to_f(scaled) + Cvt<T>::to_f(emb));
+    // separate roundings, as the eager path has them: no contraction of the scale and the add into one FMA (fp32 would differ)
+    const T scaled = Cvt<T>::from_f(__fmul_rn(Cvt<T>::to_f(src[col]), a.alpha));
+    const T emb = Cvt<T>::from_f(__fadd_rn(tw[col], pw[col]));
+    dst[col] = Cvt<T>::from_f(__fadd_rn(Cvt<T>::to_f(scaled), Cvt<T>::to_f(emb)));
   }
 }
 
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) position_bwd_kernel(const T* __restrict__
       const int col = threadIdx.x + k * blockDim.x;
       if (col < D) {
         const float g = Cvt<T>::to_f(dout[r * D + col]);
-        dseq[r * D + col] = Cvt<T>::from_f(g * alpha);
+        dseq[r * D + col] = Cvt<T>::from_f(__fmul_rn(g, alpha));
         acc[k] += g;
         atomicAdd(dpos + (long long)pi * D + col, g);
       }

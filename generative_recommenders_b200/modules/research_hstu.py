@@ -8,8 +8,10 @@ Mirrors generative_recommenders/research/modeling/sequential/hstu.py:
     silu(q k^T + rel_bias) / n under the causal mask -> u * LN(attn)  (or cat[u, a, u*a], a = LN(attn)) -> dropout ->
     Linear(+bias) + x.
 Parameter names (`_uvqk`, `_o.weight`, `_o.bias`, `_rel_attn_bias._ts_w`, `_rel_attn_bias._pos_w`) are the reference's, so
-its state dicts load unchanged.  The incremental-decoding arguments (`delta_x_offsets`, `cache`) and the
-"softmax_rel_bias" ablation are not part of this round and raise.
+its state dicts load unchanged.  Incremental decoding (`delta_x_offsets`, `cache`, `return_cache_states`, hstu.py:284-444) is
+implemented with the reference's cache layout (v jagged, padded q / k [B, n, H dqk], outputs jagged): the delta rows are
+projected, scattered into the cache, the attention is re-evaluated on the updated sequences by the same kernel and the delta rows
+are taken from it -- the same work the reference does, without the [B, H, n, n] tensors.  The "softmax_rel_bias" ablation raises.
 """
 from typing import Optional, Tuple
 
@@ -109,9 +111,8 @@ class SequentialTransductionUnitJagged(HammerModule):
     ):
         """x [sum_i N_i, D]; x_offsets [B + 1]; all_timestamps [B, n] int64 or None; invalid_attn_mask [n, n] (or [B, n, n])
         -- only its size is used: the kernel applies the causal (lower-triangular) mask the reference builds (hstu.py:626-638).
-        Returns (x', (v, None, None, x')) like the reference (padded q / k are never materialised)."""
-        if delta_x_offsets is not None or cache is not None:
-            raise NotImplementedError("incremental (cached) research forward is not built; use modules.stu.STULayer.cached_forward")
+        Returns (x', (v, padded_q, padded_k, x')) like the reference; padded q / k are only built when a cache is asked for
+        (return_cache_states=True) or updated (delta_x_offsets)."""
         kern = self.hammer_kernel()
         if kern != HammerKernel.CUDA:
             raise RuntimeError(f"generative_recommenders_b200 only implements HammerKernel.CUDA (got {kern})")
@@ -121,15 +122,43 @@ class SequentialTransductionUnitJagged(HammerModule):
             raise RuntimeError(f"invalid_attn_mask is {n} x {n} but the relative bias module was built for max_seq_len "
                                f"{self._rel_attn_bias._max_seq_len}")
         H, dqk, dv = self._num_heads, self._attention_dim, self._linear_dim
-        L = x.shape[0]
+        B = x_offsets.numel() - 1
+        delta = delta_x_offsets is not None
+        if delta:
+            # hstu.py:309-315: everything below is restricted to the rows delta_x_offsets[0]; the cache holds the rest
+            if cache is None:
+                raise RuntimeError("delta_x_offsets needs the cache of a previous call (return_cache_states=True)")
+            cached_v, cached_q, cached_k, cached_outputs = cache
+            if cached_q is None or cached_k is None:
+                raise RuntimeError("the cache was produced without return_cache_states=True: padded q / k are missing")
+            x = x[delta_x_offsets[0], :]
+        L_full = int(cached_v.shape[0]) if delta else x.shape[0]
         normed_x = layer_norm(x, self._ones_in, self._zeros_in, self._eps, kernel=kern)
         mm = _SiluFunction.apply(torch.mm(normed_x, self._uvqk.to(x.dtype)))
         u, v, q, k = torch.split(mm, [dv * H, dv * H, dqk * H, dqk * H], dim=1)
+        padded_q = padded_k = None
+        if delta or return_cache_states:
+            # row (b, position) of every jagged row -> its slot b * n + position in the padded [B * n, .] cache layout
+            lengths = x_offsets[1:] - x_offsets[:-1]
+            seq_of_row = torch.repeat_interleave(torch.arange(B, device=x.device), lengths, output_size=L_full)
+            slot_of_row = torch.arange(L_full, device=x.device) - x_offsets[:-1][seq_of_row] + seq_of_row * n
+        if delta:
+            v = cached_v.index_copy_(0, delta_x_offsets[0], v)                       # hstu.py:341-342
+            flat = delta_x_offsets[1] + torch.arange(0, B * n, n, device=x.device, dtype=delta_x_offsets[1].dtype)
+            padded_q = cached_q.view(B * n, -1).index_copy_(0, flat, q).view(B, n, -1)  # hstu.py:168-195
+            padded_k = cached_k.view(B * n, -1).index_copy_(0, flat, k).view(B, n, -1)
+            q = padded_q.view(B * n, -1)[slot_of_row]                                 # back to the jagged layout the kernel reads
+            k = padded_k.view(B * n, -1)[slot_of_row]
+        elif return_cache_states:
+            padded_q = torch.zeros(B * n, H * dqk, dtype=q.dtype, device=x.device).index_copy_(0, slot_of_row, q.detach()).view(B, n, -1)
+            padded_k = torch.zeros(B * n, H * dqk, dtype=k.dtype, device=x.device).index_copy_(0, slot_of_row, k.detach()).view(B, n, -1)
         rb = self._rel_attn_bias
         attn = hstu_rel_bias_attention(
-            n, q.reshape(L, H, dqk).contiguous(), k.reshape(L, H, dqk).contiguous(), v.reshape(L, H, dv).contiguous(), x_offsets,
-            rb._pos_w, rb._ts_w if all_timestamps is not None else None, all_timestamps,
-        ).reshape(L, H * dv)
+            n, q.reshape(L_full, H, dqk).contiguous(), k.reshape(L_full, H, dqk).contiguous(), v.reshape(L_full, H, dv).contiguous(),
+            x_offsets, rb._pos_w, rb._ts_w if all_timestamps is not None else None, all_timestamps,
+        ).reshape(L_full, H * dv)
+        if delta:
+            attn = attn[delta_x_offsets[0], :]                                       # hstu.py:421-425
         residual = x + self._o.bias.to(x.dtype)
         # u * LN(attn) [or cat(u, a, u * a), a = LN(attn): concat mode 2 of the fused kernel] -> dropout -> x + y W_o: the fused
         # output stage of the STU block (one kernel forward, one backward; nothing materialised in between)
@@ -139,4 +168,6 @@ class SequentialTransductionUnitJagged(HammerModule):
             training=self.training, concat_ux=2 if self._concat_ua else False, group_norm=False, recompute_y_in_backward=False,
             kernel=kern,
         )
-        return out, (v, None, None, out)
+        if delta:
+            out = cached_outputs.index_copy_(0, delta_x_offsets[0], out)              # hstu.py:439-442
+        return out, (v.contiguous() if return_cache_states else v, padded_q, padded_k, out)

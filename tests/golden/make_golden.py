@@ -367,8 +367,54 @@ def jagged_bmm_case(name, seed, B, max_len, K, N, dtype):
                os.path.join(HERE, f"jagged_bmm_{name}.pt"))
 
 
+def research_cache_case(seed, B, D, H, n, dqk, dv):
+    # research/modeling/sequential/hstu.py:284-444 with delta_x_offsets / cache: full forward with return_cache_states=True,
+    # then the LAST row of every sequence is replaced and only those rows are recomputed against the cache
+    from generative_recommenders.research.modeling.sequential.hstu import (
+        RelativeBucketedTimeAndPositionBasedBias,
+        SequentialTransductionUnitJagged,
+    )
+
+    torch.manual_seed(seed)
+    lengths = torch.randint(2, n + 1, (B,))
+    off = offsets_from(lengths.tolist())
+    L = int(off[-1])
+    x = torch.randn(L, D)
+    ts = torch.cumsum(torch.randint(0, 5000, (B, n)), dim=1)
+    bias_mod = RelativeBucketedTimeAndPositionBasedBias(
+        max_seq_len=n, num_buckets=128, bucketization_fn=lambda t: (torch.log(torch.abs(t).clamp(min=1)) / 0.301).long())
+    with torch.no_grad():
+        bias_mod._ts_w.normal_(0, 0.02)
+        bias_mod._pos_w.normal_(0, 0.02)
+    blk = SequentialTransductionUnitJagged(
+        embedding_dim=D, linear_hidden_dim=dv, attention_dim=dqk, dropout_ratio=0.0, attn_dropout_ratio=0.0, num_heads=H,
+        linear_activation="silu", relative_attention_bias_module=bias_mod, normalization="rel_bias", linear_config="uvqk",
+        concat_ua=False, epsilon=1e-6, max_length=n)
+    with torch.no_grad():
+        blk._uvqk.normal_(0, 0.1)
+        blk._o.bias.normal_(0, 0.1)
+    blk.eval()
+    invalid = torch.tril(torch.ones(n, n))
+    with torch.no_grad():
+        y0, cache = blk(x, off, ts, invalid, return_cache_states=True)
+        x2 = x.clone()
+        last_rows = off[1:] - 1
+        x2[last_rows] = torch.randn(B, D)
+        delta = (last_rows.clone(), (lengths - 1).clone())
+        cache_in = tuple(t.clone() for t in cache)
+        y1, cache1 = blk(x2, off, ts, invalid, delta_x_offsets=delta, cache=tuple(t.clone() for t in cache))
+        y_full, _ = blk(x2, off, ts, invalid)  # what a full forward on the updated input gives (rows other than the last differ only
+        #                                        through the cache semantics: they keep their cached outputs)
+    torch.save(dict(n=n, H=H, D=D, dqk=dqk, dv=dv, x=x, x2=x2, seq_offsets=off, timestamps=ts, delta_rows=delta[0], delta_pos=delta[1],
+                    state_dict={k: v.detach().clone() for k, v in blk.state_dict().items()}, y0=y0, cache0=cache_in, y1=y1,
+                    cache1=tuple(t.clone() for t in cache1), y_full=y_full),
+               os.path.join(HERE, "research_block_cache.pt"))
+
+
 def main():
     only = set(sys.argv[1:])
+    if not only or "research_cache" in only:
+        research_cache_case(75, 3, 32, 2, 24, 16, 16)
     if not only or "jagged_bmm" in only:
         jagged_bmm_case("f32", 95, 5, 40, 24, 36, torch.float32)
         jagged_bmm_case("bf16", 96, 4, 70, 64, 80, torch.bfloat16)

@@ -60,3 +60,28 @@ def test_research_block_dropout_and_eval_are_consistent():
     blk.train()
     yt, _ = blk(*args)
     assert torch.isfinite(yt).all() and not torch.equal(yt, y0)
+
+
+def test_research_block_cached_delta_forward_golden():
+    """Incremental decoding (hstu.py:284-444 with delta_x_offsets / cache): a full forward that returns its cache states, then the
+    last row of every sequence is replaced and only those rows are recomputed against the cache.  Outputs and all four cache
+    tensors against the unmodified reference module."""
+    g = golden("research_block_cache.pt")
+    g = dict(g, concat_ua=False, eps=1e-6)
+    blk = _build(g).eval()
+    n = g["n"]
+    mask = torch.tril(torch.ones(n, n, device=DEV))
+    off, ts = g["seq_offsets"].to(DEV), g["timestamps"].to(DEV)
+    with torch.no_grad():
+        y0, cache = blk(g["x"].to(DEV), off, ts, mask, return_cache_states=True)
+        assert_rel(y0, g["y0"], "cached: first full forward")
+        for name, a, r in zip(("v", "padded_q", "padded_k", "outputs"), cache, g["cache0"]):
+            assert a.shape == r.shape, name
+            assert_rel(a, r, f"cache state {name} after the full forward")
+        delta = (g["delta_rows"].to(DEV), g["delta_pos"].to(DEV))
+        y1, cache1 = blk(g["x2"].to(DEV), off, ts, mask, delta_x_offsets=delta, cache=cache)
+    assert_rel(y1, g["y1"], "cached: delta forward output")
+    for name, a, r in zip(("v", "padded_q", "padded_k", "outputs"), cache1, g["cache1"]):
+        assert_rel(a, r, f"cache state {name} after the delta forward")
+    # the recomputed rows equal what a full forward on the updated input gives for those rows
+    assert_rel(y1[delta[0]], g["y_full"][g["delta_rows"]], "delta rows vs full forward")

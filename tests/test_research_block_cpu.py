@@ -52,8 +52,8 @@ def test_no_cpu_fallback():
     off = torch.tensor([0, 4, 10])
     with pytest.raises(RuntimeError):
         blk(x, off, None, torch.tril(torch.ones(24, 24)))
-    with pytest.raises(NotImplementedError):
-        blk(x, off, None, torch.tril(torch.ones(24, 24)), delta_x_offsets=(off, off), cache=(None,) * 4)
+    with pytest.raises(RuntimeError):  # a delta call needs a cache that carries padded q / k
+        blk(x, off, None, torch.tril(torch.ones(24, 24)), delta_x_offsets=(off[:2], off[:2]), cache=(x, None, None, x))
 
 
 def test_non_causal_mask_and_wrong_sizes_are_rejected():
