@@ -81,20 +81,32 @@ struct BwdCfg {
   // 128 key rows x 64 query rows; after the elementwise stage the front of the S^T half holds P^T as bf16), the dV and
   // dK accumulators and NDQ dQ accumulators (tile i -> buffer i % NDQ; with two, the warpgroups drain dQ two tiles late and
   // never wait for it).  d = 128 fills TMEM with one slot and one dQ accumulator: 128 + 3 * 128 columns.
-  static constexpr int NSLOT = (D <= 32) ? 3 : (D == 64 ? 2 : 1);
-  static constexpr int NDQ = (D <= 64) ? 2 : 1;
+  //
+  // TILE mode (d <= 64), r02: the half-tile units above made the issuer of the scores wait for the dV GEMM of three units
+  // earlier (the slot holds P^T until then): a dependency cycle X -> elementwise -> YV -> X of ~3700 clk per three units that
+  // set the pace of the whole CTA (profiles/r02_bwd_timeline_units.txt).  In TILE mode there is ONE score slot for a whole query
+  // tile {S^T: 128 columns | dP^T: 128 columns}, written by N = 128 MMAs (64 clk each instead of 2 x 48 for two N = 64 halves),
+  // and P^T goes to its own small ring (NP buffers of 64 columns): the slot is free again as soon as the four elementwise
+  // warpgroups have LOADED it (scores_free), half way through their work, not after the dV GEMM.  d = 128 keeps the units: its
+  // dK / dV accumulators leave no room for a second tensor of scores.
+  static constexpr bool TILE = D <= 64;
+  static constexpr int NSLOT = TILE ? 2 : 1;     // unit mode: score slots of 128 columns (TILE mode: the one 256-column slot)
+  static constexpr int NP = (D <= 32) ? 2 : 1;   // TILE mode: P^T buffers (tile i -> i % NP)
+  static constexpr int NDQ = (D <= 32) ? 2 : 1;
   // s_full barrier instances: unit u -> [u % NSF].  At least two even with one slot: the warpgroups alternate units, and a
   // warpgroup must never wait for phase k+1 of a barrier before phase k has completed (the parity test would pass at once).
   static constexpr int NSF = NSLOT < 2 ? 2 : NSLOT;
   static constexpr int LAG = NDQ;                // the warpgroups drain dQ of tile i - LAG after their unit of tile i
   static constexpr int TMEM_SLOT = 0;
-  static constexpr int TMEM_DV = NSLOT * 128;
+  static constexpr int TMEM_S = 0, TMEM_DP = 128, TMEM_P = 256;  // TILE mode
+  static constexpr int TMEM_DV = TILE ? 256 + NP * 64 : NSLOT * 128;
   static constexpr int TMEM_DK = TMEM_DV + D;
   static constexpr int TMEM_DQ = TMEM_DK + D;   // NDQ buffers of D columns
   static_assert(TMEM_DQ + NDQ * D <= 512, "TMEM budget");
   // scripts/sim_bwd_protocol.py: a 3-slot score ring needs the Q/dO ring to be at least 4 deep (the scores of tile i+2 are
   // requested before tile i releases its stage), otherwise the producer and the MMA issuer wait on each other.
   static_assert(NSLOT != 3 || STAGES >= 4, "3-slot score ring needs >= 4 Q/dO stages");
+  static_assert(!TILE || STAGES >= 3, "TILE mode: tile i + 1 is staged while tile i is in flight and tile i - 1 drains");
 };
 
 struct BwdBars {
@@ -105,6 +117,9 @@ struct BwdBars {
   uint64_t tile_done[4];  // tile i -> [i % 4]: both issuers have finished every GEMM of query tile i (count 2)
   uint64_t slot_free[3];  // unit u -> [u % NSLOT]: dV of the unit has consumed P^T in the slot
   uint64_t dq_empty[2], fin_full;
+  // TILE mode: scores_free (4 x 128 arrivals: every elementwise thread has loaded its part of the score slot),
+  // tile_ready[i & 1] (4 x 128: P^T and dS^T of tile i are written), p_free[i % NP] (YV: dV of the tile has consumed P^T)
+  uint64_t scores_free, tile_ready[2], p_free[2];
   uint32_t tmem_base;
 };
 
@@ -232,6 +247,11 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
     mbar_init(&bars->kv_ready, 128);
     for (int i = 0; i < 4; ++i) mbar_init(&bars->q_ready[i], 128);
     for (int i = 0; i < 3; ++i) mbar_init(&bars->slot_free[i], 1);
+    mbar_init(&bars->scores_free, 512);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->tile_ready[i], 512);
+      mbar_init(&bars->p_free[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
@@ -265,6 +285,39 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
       const uint64_t ddo_k = desc_kmajor<SW>(smem_u32(sDO), 0);                      // dO_i rows as K-major B
       mbar_wait(kv_rdy, 0);
       tc_fence_after_sync();
+      if (Cfg::TILE) {
+        // one score slot per query tile, N = 128: S^T = K Q_i^T into columns [0, 128), dP^T = V dO_i^T into [128, 256)
+        constexpr uint32_t idesc_t = make_idesc(128, 128, false, false, false, false);
+        for (int i = 0; i < T; ++i) {
+          const int st = i % NST;
+          if (leader) HSTU_TSTAMP(0, i, 0);
+          if (i >= 1) {  // every elementwise thread has loaded its part of the scores of tile i - 1
+            mbar_wait(&bars->scores_free, (i - 1) & 1);
+            tc_fence_after_sync();
+          }
+          mbar_wait(&q_rdy[st], (i / NST) & 1);
+          tc_fence_after_sync();
+          const uint64_t tile_off = (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
+          if (leader) {
+            HSTU_TSTAMP(0, i, 1);
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks) {
+              const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
+              const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
+              mma_ss(tmem + Cfg::TMEM_S, dk_k + o, dq_k + tile_off + o, idesc_t, ks > 0);
+            }
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks) {
+              const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
+              const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
+              mma_ss(tmem + Cfg::TMEM_DP, dv_k + o, ddo_k + tile_off + o, idesc_t, ks > 0);
+            }
+            mma_commit(&bars->s_full[0]);
+            HSTU_TSTAMP(0, i, 2);
+          }
+          __syncwarp();
+        }
+      } else
       for (int u = 0; u < U; ++u) {
         const int i = u >> 1, hf = u & 1, st = i % NST, slot = u % NSLOT;
         if (leader) HSTU_TSTAMP(0, u, 0);
@@ -302,6 +355,26 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
       // ---- issuer YV: dV += P^T dO (A = P^T from the unit's TMEM slot) of every unit; its commit frees the slot ----
       constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, false, false);   // A = P^T from TMEM, B MN-major (fp16 x fp16)
       const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
+      if (Cfg::TILE) {
+        for (int i = 0; i < T; ++i) {
+          const int st = i % NST, pbuf = i % Cfg::NP;
+          if (leader) HSTU_TSTAMP(1, i, 0);
+          mbar_wait(&bars->tile_ready[i & 1], (i >> 1) & 1);  // P^T (TMEM) and dS^T (shared memory) of the tile are written
+          tc_fence_after_sync();
+          const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
+          const uint32_t tp = tmem + Cfg::TMEM_P + pbuf * 64;
+          if (leader) {
+            HSTU_TSTAMP(1, i, 1);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)  // K = the 128 query rows of the tile; 16 fp16 of P^T per 8 TMEM columns
+              mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (i > 0) || (ks > 0));
+            mma_commit(&bars->p_free[pbuf]);        // the elementwise warpgroups may overwrite this P^T buffer
+            mma_commit(&bars->tile_done[i & 3]);    // this issuer is done with dO_i
+            HSTU_TSTAMP(1, i, 2);
+          }
+          __syncwarp();
+        }
+      } else
       for (int u = 0; u < U; ++u) {
         const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1, slot = u % NSLOT;
         // P^T / dS^T of the unit are written.  One barrier per (half, tile parity): with a 3-slot score ring a warpgroup may
@@ -331,6 +404,26 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
       constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, false, false);   // A = dS^T K-major, B MN-major (fp16 x fp16)
       const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box [kv][q] as K-major A
       const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
+      if (Cfg::TILE) {
+        for (int i = 0; i < T; ++i) {
+          const int st = i % NST, pb = i & 1;
+          if (leader) HSTU_TSTAMP(4, i, 0);
+          mbar_wait(&bars->tile_ready[pb], (i >> 1) & 1);
+          tc_fence_after_sync();
+          const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
+          if (leader) {
+            HSTU_TSTAMP(4, i, 1);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {  // K = 128 query rows: box ks / 4 of the pair, 32 bytes per step inside the box
+              const uint64_t box = (uint64_t)((pb * Cfg::PT_BYTES + (ks >> 2) * 16384 + (ks & 3) * 32) >> 4);
+              mma_ss(tmem + Cfg::TMEM_DK, dds_k + box, dq_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (i > 0) || (ks > 0));
+            }
+            mma_commit(&bars->tile_done[i & 3]);
+            HSTU_TSTAMP(4, i, 2);
+          }
+          __syncwarp();
+        }
+      } else
       for (int u = 0; u < U; ++u) {
         const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1;
         if (leader) HSTU_TSTAMP(4, u, 0);
@@ -359,8 +452,12 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
       mbar_wait(kv_rdy, 0);
       for (int i = 0; i < T; ++i) {
         const int pb = i & 1;
-        mbar_wait(&bars->unit_done[0 * 2 + pb], (i >> 1) & 1);
-        mbar_wait(&bars->unit_done[1 * 2 + pb], (i >> 1) & 1);
+        if (Cfg::TILE) {
+          mbar_wait(&bars->tile_ready[pb], (i >> 1) & 1);
+        } else {
+          mbar_wait(&bars->unit_done[0 * 2 + pb], (i >> 1) & 1);
+          mbar_wait(&bars->unit_done[1 * 2 + pb], (i >> 1) & 1);
+        }
         if (i >= Cfg::NDQ) mbar_wait(&bars->dq_empty[i % Cfg::NDQ], ((i / Cfg::NDQ) - 1) & 1);  // dQ_{i-NDQ} has been drained from this accumulator
         tc_fence_after_sync();
         if (leader) {
@@ -486,7 +583,8 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
       const int u = 2 * i + hf, slot = u % Cfg::NSLOT;
       const int m0 = q_tile(i) * 128;
       if (stamp) HSTU_TSTAMP(2 + hf, i, 0);
-      mbar_wait(&bars->s_full[u % Cfg::NSF], (u / Cfg::NSF) & 1);
+      if (Cfg::TILE) mbar_wait(&bars->s_full[0], i & 1);
+      else mbar_wait(&bars->s_full[u % Cfg::NSF], (u / Cfg::NSF) & 1);
       tc_fence_after_sync();
       if (stamp) HSTU_TSTAMP(2 + hf, i, 1);
       // classification of this half-tile (uniform over the two warpgroups of the unit)
@@ -496,8 +594,10 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
       const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + hf * 16384);
       const int jr = j_pos - m0 - cbase;           // query column (relative to the half) equal to j
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
-      const uint32_t st_addr = tmem + Cfg::TMEM_SLOT + slot * 128 + lane_bits;
-      const uint32_t dp_addr = st_addr + 64;
+      // TILE mode: the score slot holds the whole tile (this half starts at column cbase of S^T and of dP^T); unit mode: the
+      // slot holds one half-tile {S^T | dP^T}
+      const uint32_t st_addr = tmem + (Cfg::TILE ? Cfg::TMEM_S + cbase : Cfg::TMEM_SLOT + slot * 128) + lane_bits;
+      const uint32_t dp_addr = tmem + (Cfg::TILE ? Cfg::TMEM_DP + cbase : Cfg::TMEM_SLOT + slot * 128 + 64) + lane_bits;
 #pragma unroll
       for (int sc = 0; sc < 2; ++sc) {  // 2 sub-chunks of 16 query columns
         const int col0 = cc * 32 + sc * 16;
@@ -505,6 +605,10 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
         tmem_ld16(st_addr + col0, s);
         tmem_ld16(dp_addr + col0, dp);
         tmem_ld_wait();
+        if (Cfg::TILE && sc == 1) {  // this thread has loaded all of its scores: the issuer may overwrite the slot (tile i + 1)
+          tc_fence_before_sync();
+          mbar_arrive(&bars->scores_free);
+        }
         uint32_t pp[8], dd[8];
         // p = x sig(x) and g = sig (1 + x (1 - sig)) from one tanh: x = 2 hh, sig = (1 + t) / 2
         // packed fp32x2 arithmetic (FMUL2 / FFMA2): two elements per issued instruction, one MUFU.TANH per element
@@ -559,9 +663,18 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
         }
 #undef HSTU_BWD_ELEM2
         if (sc == 0 && i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
-        // P^T of these 16 query columns (16 fp16 = 8 TMEM columns) goes to columns [32 cc + 8 sc, + 8) of the slot: a part of
-        // THIS warpgroup's S^T region that it has already read (the neighbour warpgroup reads / writes only [32 (1-cc), +32))
-        tmem_st8(st_addr + cc * 32 + sc * 8, pp);
+        if (Cfg::TILE) {
+          // P^T has its own ring: buffer i % NP, the 16 fp16 of these query columns at columns [16 wg + 8 sc, + 8)
+          if (sc == 0 && i >= Cfg::NP) {
+            mbar_wait(&bars->p_free[i % Cfg::NP], ((i / Cfg::NP) - 1) & 1);  // dV of tile i - NP has consumed the buffer
+            tc_fence_after_sync();
+          }
+          tmem_st8(tmem + Cfg::TMEM_P + (i % Cfg::NP) * 64 + lane_bits + wg * 16 + sc * 8, pp);
+        } else {
+          // P^T of these 16 query columns (16 fp16 = 8 TMEM columns) goes to columns [32 cc + 8 sc, + 8) of the slot: a part of
+          // THIS warpgroup's S^T region that it has already read (the neighbour warpgroup reads / writes only [32 (1-cc), +32))
+          tmem_st8(st_addr + cc * 32 + sc * 8, pp);
+        }
         // dS^T [kv][q] (16-byte stores): A of dK as stored, A of dQ read MN-major
         st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, cc * 4 + sc * 2), dd[0], dd[1], dd[2], dd[3]);
         st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, cc * 4 + sc * 2 + 1), dd[4], dd[5], dd[6], dd[7]);
@@ -570,7 +683,8 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
       tc_fence_before_sync();
       fence_proxy_async_smem();
       if (stamp) HSTU_TSTAMP(2 + hf, i, 2);
-      mbar_arrive(&bars->unit_done[hf * 2 + (i & 1)]);
+      if (Cfg::TILE) mbar_arrive(&bars->tile_ready[i & 1]);
+      else mbar_arrive(&bars->unit_done[hf * 2 + (i & 1)]);
     }
     // ---------------- epilogue: dV (warpgroup 0) / dK (warpgroup 1): TMEM -> scale -> global ----------------
     mbar_wait(&bars->fin_full, 0);

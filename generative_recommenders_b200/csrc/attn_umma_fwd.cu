@@ -13,10 +13,13 @@
 //   warps 4-7, 8-11: two "silu" warpgroups.  Warpgroup g owns key tiles t = g, g+2, ...: tcgen05.ld S (one query row per
 //                    thread, next 32 columns prefetched), p = silu(alpha*s) * mask via one MUFU (tanh) + packed fp32x2
 //                    FMUL2 / FFMA2, packs bf16 pairs and writes them with tcgen05.st over the S columns already read.
-//   warps 12-15    : (bf16 inputs only) converter warpgroup: kind::f16 needs ONE operand format per instruction and the parity
-//                    budget needs P in fp16 (11-bit significand; a bf16 P alone costs 1.7e-3 of relative error), so bf16 Q / K / V
-//                    tiles are converted to fp16 IN PLACE in shared memory when their TMA load lands (exact for every bf16
-//                    value in the fp16 range) and all MMAs of the kernel run on fp16 operands.  fp16 inputs skip this stage.
+//   warps 12-15    : (bf16 inputs only) converter warpgroup: kind::f16 needs ONE operand format per instruction (a mixed fp16 x
+//                    bf16 descriptor is an illegal instruction on B200) and the parity budget needs P in fp16 (11-bit
+//                    significand; a bf16 P alone costs 1.7e-3 of relative error).  So the V tiles -- the B operand of P.V --
+//                    are converted bf16 -> fp16 IN PLACE in shared memory when their TMA load lands (exact for every bf16
+//                    value in the fp16 range); S = Q K^T stays bf16 x bf16.  V has slack (it is needed only after the silu
+//                    stage), so the hop is off the critical path; its cost is shared-memory bandwidth (one read + one write of
+//                    the tile).  fp16 inputs skip this stage.
 // The 1/N factor of the reference is applied once in the epilogue (O tile: TMEM -> registers -> 128-bit global stores,
 // rows past the sequence end are not written).  Rows of neighbouring sequences that a 128-row TMA box drags in are
 // neutralised by the mask (P = 0 for key positions >= len), never by re-reading memory.
@@ -74,7 +77,7 @@ struct FwdCfg {
 struct FwdBars {
   uint64_t q_full;
   uint64_t k_full[3], v_full[3];
-  uint64_t q_ready, k_ready[3], v_ready[3];  // bf16 inputs: the tile has been converted to fp16 (128 converter threads)
+  uint64_t v_ready[3];  // bf16 inputs: the V tile has been converted to fp16 (128 converter threads)
   uint64_t s_full[3], p_full[3], pv_done[3];
   uint64_t o_full;
   uint32_t tmem_base;
@@ -83,7 +86,7 @@ struct FwdBars {
 template <int D, bool BF16>
 __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(const __grid_constant__ FwdParams p) {
   using Cfg = FwdCfg<D>;
-  constexpr bool CONV = BF16;  // bf16 tiles are converted to fp16 in shared memory; every MMA below is fp16 x fp16
+  constexpr bool CONV = BF16;  // bf16 V tiles are converted to fp16 in shared memory: P.V runs fp16 x fp16
   constexpr int SW = Cfg::SW;
   constexpr int NST = Cfg::STAGES;
   constexpr int NSL = Cfg::NSLOT;
@@ -120,10 +123,8 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
       mbar_init(&bars->s_full[i], 1);
       mbar_init(&bars->p_full[i], 128);
       mbar_init(&bars->pv_done[i], 1);
-      mbar_init(&bars->k_ready[i], 128);
       mbar_init(&bars->v_ready[i], 128);
     }
-    mbar_init(&bars->q_ready, 128);
     mbar_init(&bars->o_full, 1);
     fence_barrier_init();
   }
@@ -132,8 +133,8 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
-  uint64_t* const q_rdy = CONV ? &bars->q_ready : &bars->q_full;
-  uint64_t* const k_rdy = CONV ? bars->k_ready : bars->k_full;
+  uint64_t* const q_rdy = &bars->q_full;
+  uint64_t* const k_rdy = bars->k_full;
   uint64_t* const v_rdy = CONV ? bars->v_ready : bars->v_full;
   // bf16 inputs run 512 threads (128 registers / thread at launch): per-warpgroup budgets are set at the top of each role
 
@@ -141,16 +142,8 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
     // ---------------- converter warpgroup (bf16 inputs): TMA-landed tile -> fp16 in place -> ready ----------------
     reg_dealloc<64>();
     const int t = tid - 384;
-    mbar_wait(&bars->q_full, 0);
-    convert_bf16_to_f16_inplace<128>(sQ, Cfg::TILE_BYTES, t, 1.0f);
-    fence_proxy_async_smem();
-    mbar_arrive(&bars->q_ready);
     for (int i = 0; i < T; ++i) {
       const int st = i % NST;
-      mbar_wait(&bars->k_full[st], (i / NST) & 1);
-      convert_bf16_to_f16_inplace<128>(sK + st * Cfg::TILE_BYTES, Cfg::TILE_BYTES, t, 1.0f);
-      fence_proxy_async_smem();
-      mbar_arrive(&bars->k_ready[st]);
       mbar_wait(&bars->v_full[st], (i / NST) & 1);
       convert_bf16_to_f16_inplace<128>(sV + st * Cfg::TILE_BYTES, Cfg::TILE_BYTES, t, 1.0f);
       fence_proxy_async_smem();
@@ -211,7 +204,7 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
     // descriptors are built once and only their address field is advanced.  One commit per tile and thread: K / V stages
     // are released through the slot barriers (stage = slot = tile % 3).
     const bool leader = lane == 0;
-    constexpr uint32_t idesc_qk = make_idesc(128, 128, false, false, false, false);  // fp16 x fp16 (see the header comment)
+    constexpr uint32_t idesc_qk = make_idesc(128, 128, false, false, BF16, BF16);    // Q, K in the input dtype
     const uint64_t dq0 = desc_kmajor<SW>(smem_u32(sQ), 0);
     const uint64_t dk0 = desc_kmajor<SW>(smem_u32(sK), 0);
     mbar_wait(q_rdy, 0);

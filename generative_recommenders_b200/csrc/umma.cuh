@@ -276,15 +276,27 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
 template <int NT>
 __device__ __forceinline__ void convert_bf16_to_f16_inplace(uint8_t* base, int bytes, int t, float scale) {
   const uint32_t s0 = smem_u32(base);
-  for (int off = t * 16; off < bytes; off += NT * 16) {
-    uint32_t w[4];
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(s0 + off));
+  constexpr int U = 4;  // independent 16-byte chunks in flight per thread (the loop is latency-bound otherwise)
+  for (int off0 = t * 16; off0 < bytes; off0 += U * NT * 16) {
+    uint32_t w[U][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float lo = __uint_as_float(w[i] << 16) * scale, hi = __uint_as_float(w[i] & 0xffff0000u) * scale;
-      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(hi), "f"(lo));
+    for (int u = 0; u < U; ++u) {
+      const int off = off0 + u * NT * 16;
+      if (off < bytes)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]) : "r"(s0 + off));
     }
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + off), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int off = off0 + u * NT * 16;
+      if (off < bytes) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float lo = __uint_as_float(w[u][i] << 16) * scale, hi = __uint_as_float(w[u][i] & 0xffff0000u) * scale;
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[u][i]) : "f"(hi), "f"(lo));
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s0 + off), "r"(w[u][0]), "r"(w[u][1]), "r"(w[u][2]), "r"(w[u][3]) : "memory");
+      }
+    }
   }
 }
 

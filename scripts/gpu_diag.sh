@@ -18,7 +18,7 @@ timeout 300 python bench.py --workload attn --batch 512 --attn-heads 4 --attn-di
 
 HSTU_EXP="HSTU_TRACE" timeout 400 python -m generative_recommenders_b200.build --force > gpurun_out/trace_build.log 2>&1
 bash scripts/gpu_trace.sh > gpurun_out/trace_run.log 2>&1
-python scripts/trace_report.py gpurun_out/bwd_trace.txt 20 8 > gpurun_out/bwd_timeline.txt 2>&1
+python scripts/trace_report.py gpurun_out/bwd_trace.txt 10 4 > gpurun_out/bwd_timeline.txt 2>&1
 echo "== selftest"; tail -5 gpurun_out/selftest_pytest.log | cut -c1-300
 echo "== mixed probe"; tail -8 gpurun_out/mixed_probe.log | cut -c1-300
 echo "== pytest"; tail -40 gpurun_out/pytest_gpu_full.log | cut -c1-330

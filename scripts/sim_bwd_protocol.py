@@ -29,10 +29,136 @@ class Violation(Exception):
 
 
 def cfg_for(d):
+    # unit mode of the kernel (d = 128 in the product; the d = 32 / 64 rows describe the r01 configuration and are only used by
+    # the two bug-reproduction tests)
     return dict(NST={32: 4, 64: 3, 128: 1}[d], NSLOT={32: 3, 64: 2, 128: 1}[d], NDQ={32: 2, 64: 2, 128: 1}[d])
 
 
+def run_tile(T, d, seed):
+    """TILE mode of the kernel (d <= 64): one score slot per query tile, P^T ring of NP buffers, NDQ dQ accumulators."""
+    NST = {32: 4, 64: 3}[d]
+    NP = NDQ = {32: 2, 64: 1}[d]
+    rnd = random.Random(seed)
+    B = {"kv": Bar(1), "kvr": Bar(1), "fin": Bar(2), "sf": Bar(1), "free": Bar(4)}
+    for i in range(4):
+        B[f"qf{i}"], B[f"qr{i}"], B[f"td{i}"] = Bar(1), Bar(1), Bar(3)
+    for i in range(2):
+        B[f"tr{i}"], B[f"pf{i}"], B[f"dqe{i}"] = Bar(4), Bar(1), Bar(1)
+
+    def X():
+        yield ("wait", "kvr", 0)
+        for i in range(T):
+            if i >= 1:
+                yield ("wait", "free", i - 1)
+            yield ("wait", f"qr{i % NST}", i // NST)
+            yield ("async", "sf")
+
+    def YV():
+        for i in range(T):
+            yield ("wait", f"tr{i & 1}", i >> 1)
+            yield ("async", f"pf{i % NP}")
+            yield ("async", f"td{i & 3}")
+        yield ("async", "fin")
+
+    def YK():
+        for i in range(T):
+            yield ("wait", f"tr{i & 1}", i >> 1)
+            yield ("async", f"td{i & 3}")
+        yield ("async", "fin")
+
+    def Z():
+        yield ("wait", "kvr", 0)
+        for i in range(T):
+            yield ("wait", f"tr{i & 1}", i >> 1)
+            if i >= NDQ:
+                yield ("wait", f"dqe{i % NDQ}", i // NDQ - 1)
+            yield ("async", f"td{i & 3}")
+
+    def W():
+        for i in range(T):
+            yield ("wait", "sf", i)
+            # sub-chunk 0: load, compute, then the stores wait for the dS^T box pair and the P^T buffer
+            if i >= 2:
+                yield ("wait", f"td{(i - 2) & 3}", (i - 2) >> 2)
+            if i >= NP:
+                yield ("wait", f"pf{i % NP}", i // NP - 1)
+            yield ("arrive", "free")        # sub-chunk 1 loaded: the score slot may be overwritten
+            yield ("arrive", f"tr{i & 1}")
+        yield ("wait", "fin", 0)
+
+    def Dr():
+        yield ("async", "kv")
+        for i in range(min(NST, T)):
+            yield ("async", f"qf{i % NST}")
+        yield ("wait", "kv", 0)
+        yield ("arrive", "kvr")
+        for i in range(min(NST, T)):
+            yield ("wait", f"qf{i % NST}", i // NST)
+            yield ("arrive", f"qr{i % NST}")
+        for i in range(T):
+            yield ("wait", f"td{i & 3}", i >> 2)
+            if i + NST < T:
+                yield ("async", f"qf{(i + NST) % NST}")
+            yield ("arrive", f"dqe{i % NDQ}")
+            if i + NST < T:
+                yield ("wait", f"qf{(i + NST) % NST}", (i + NST) // NST)
+                yield ("arrive", f"qr{(i + NST) % NST}")
+
+    actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W0": W(), "W1": W(), "W2": W(), "W3": W(), "D": Dr()}
+    return _simulate(actors, B, rnd)
+
+
+def _simulate(actors, B, rnd):
+    pending = {k: None for k in actors}
+    queues = {k: [] for k in actors}
+    done = set()
+    steps = 0
+    while len(done) < len(actors) or any(queues.values()):
+        steps += 1
+        if steps > 400000:
+            raise Violation("no progress (livelock?)")
+        choices = [("run", k) for k in actors if k not in done] + [("fire", k) for k, q in queues.items() if q]
+        rnd.shuffle(choices)
+        progressed = False
+        for kind, k in choices:
+            if kind == "fire":
+                B[queues[k].pop(0)].arrive()
+                progressed = True
+                break
+            if pending[k] is None:
+                try:
+                    pending[k] = next(actors[k])
+                except StopIteration:
+                    done.add(k)
+                    progressed = True
+                    break
+            op = pending[k]
+            if op[0] == "wait":
+                _, name, want = op
+                bar = B[name]
+                passes = (bar.phase & 1) != (want & 1)
+                if passes and bar.phase <= want:
+                    raise Violation(f"{k}: wait on {name} for phase {want} passed while the barrier is in phase {bar.phase} (false pass)")
+                if not passes and bar.phase > want:
+                    raise Violation(f"{k}: wait on {name} for phase {want} but the barrier is already in phase {bar.phase} (two ahead)")
+                if not passes:
+                    continue
+            elif op[0] == "arrive":
+                B[op[1]].arrive()
+            elif op[0] == "async":
+                queues[k].append(op[1])
+            pending[k] = None
+            progressed = True
+            break
+        if not progressed:
+            state = {k: pending[k] for k in actors if k not in done}
+            raise Violation(f"deadlock: {state}")
+    return steps
+
+
 def run(T, d, seed, break_ud=False, break_sf=False):
+    if d in (32, 64) and not (break_ud or break_sf):
+        return run_tile(T, d, seed)
     c = cfg_for(d)
     NST, NSLOT, NDQ = c["NST"], c["NSLOT"], c["NDQ"]
     NSF = NSLOT if break_sf else max(NSLOT, 2)
