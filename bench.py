@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--attn-heads", type=int, default=4)
     ap.add_argument("--attn-impl", type=int, default=0, help="0 auto, 1 generic kernels, 2 force tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch sequences per GPU (default, what the driver's scaling run measures); strong: --batch "
+                         "sequences in total, sharded over the ranks balanced by sum(len^2) (distributed.shard_sequences)")
     return ap.parse_args()
 
 
@@ -181,6 +184,17 @@ def run_ours(args):
     # and not a straggler); the activations / gradients differ per rank (seeded below)
     lengths, nt, off = synth_lengths(args.batch, args.lmax, dev, 1001)
     torch.cuda.manual_seed(4321 + rank)  # dropout masks: CUDA generator, different per rank
+    seqs_total = args.batch * world
+    if args.scaling == "strong" and world > 1:
+        # fixed global batch: this rank keeps its shard of the SAME seeded batch (balanced by attention cost)
+        from generative_recommenders_b200.distributed import shard_sequences
+
+        mine = shard_sequences(lengths.tolist(), world)[rank]
+        idx = torch.tensor(mine, device=dev, dtype=torch.long)
+        lengths, nt = lengths[idx], nt[idx]
+        off = torch.zeros(len(mine) + 1, dtype=torch.int64, device=dev)
+        off[1:] = torch.cumsum(lengths, 0)
+        seqs_total = args.batch
     L = int(off[-1])
 
     if args.workload == "hstu_large":
@@ -221,11 +235,11 @@ def run_ours(args):
                 return float(loss.item())  # device -> host read of the step result
             return loss
 
-        units_per_step = args.batch
+        units_per_step = seqs_total / world
         d2h_bytes = 4
         cfg = {"workload": f"HSTU-large stack fwd+bwd+AdamW: {layers} layers, D=256, H=8, dqk=dv=32, bf16, Lmax={args.lmax}, "
-                           f"{args.batch} user sequences/GPU (lengths U[0.9,1.0)*Lmax, 1-20 targets, seed 1001 on every rank; activations seeded per rank), dropout 0.2",
-               "global_batch": args.batch * world, "seq_len": args.lmax, "rows_per_gpu": L,
+                           f"{args.batch} user sequences{'/GPU' if args.scaling == 'weak' else ' in total (sharded by sum len^2)'} (lengths U[0.9,1.0)*Lmax, 1-20 targets, seed 1001 on every rank; activations seeded per rank), dropout 0.2",
+               "global_batch": seqs_total, "seq_len": args.lmax, "rows_per_gpu": L,
                "parallelism": f"dp{world} (batch-sharded, per-layer in-place bf16 NCCL all-reduce of the flat gradient bucket overlapped with backward)",
                "l2": f"inputs + activations per step ({L * D * 2 * 6 / 1e6:.0f} MB+) exceed the 126 MB L2; no explicit flush"}
         cfg["attn_shape"] = {"batch": args.batch, "lmax": args.lmax, "heads": H, "d": dh}
@@ -312,7 +326,7 @@ def run_ours(args):
         "metric": "user-seqs/sec HSTU-large L=8192 d=256 bf16 fwd+bwd" if args.workload == "hstu_large" else
                   "user-seqs/sec hstu_mha fwd+bwd microbench",
         "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": cfg,
         "e2e": {"value": value_e2e, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},

@@ -117,8 +117,8 @@ struct BwdBars {
   uint64_t tile_done[4];  // tile i -> [i % 4]: both issuers have finished every GEMM of query tile i (count 2)
   uint64_t slot_free[3];  // unit u -> [u % NSLOT]: dV of the unit has consumed P^T in the slot
   uint64_t dq_empty[2], fin_full;
-  // TILE mode: scores_free (4 x 128 arrivals: every elementwise thread has loaded its part of the score slot),
-  // tile_ready[i & 1] (4 x 128: P^T and dS^T of tile i are written), p_free[i % NP] (YV: dV of the tile has consumed P^T)
+  // TILE mode: scores_free (2 x 128 arrivals: every elementwise thread has loaded its part of the score slot),
+  // tile_ready[i & 1] (2 x 128: P^T and dS^T of tile i are written), p_free[i % NP] (YV: dV of the tile has consumed P^T)
   uint64_t scores_free, tile_ready[2], p_free[2];
   uint32_t tmem_base;
 };
@@ -183,15 +183,16 @@ __global__ void dout_amax_kernel(const uint16_t* __restrict__ dout, long long ro
 
 __device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-// 768 threads = 6 warpgroups with their own register budgets (setmaxnreg; 80 regs / thread at launch, and the CTA can only
-// redistribute THAT pool: increases beyond it would spin forever in setmaxnreg.inc):
-//   warps 0-3    issuers X (scores), YV (dV), YK (dK), Z (dQ): one elected lane each                      -> 56 regs
-//   warps 4-19   FOUR elementwise warpgroups: warpgroup w handles 32 of the 64 query columns (chunk w & 1) of the units of
-//                half w >> 1.  Four warps per scheduler instead of two: the stage is bound by MUFU + dependent-issue latency,
-//                and with two warps per scheduler the MUFU pipe sat idle 40 % of the time (r02 timeline)      -> 80 regs
-//   warps 20-23  dQ drain warpgroup; its elected lane is also the TMA producer; converts bf16 tiles to fp16 -> 96 regs
+// 512 threads = 4 warpgroups with their own register budgets (setmaxnreg; 128 regs / thread at launch -- a CTA can only
+// redistribute the pool it was launched with: requests beyond it spin forever in setmaxnreg.inc):
+//   warps 0-3    issuers X (scores), YV (dV), YK (dK), Z (dQ): one elected lane each                          -> 64 regs
+//   warps 4-11   two elementwise warpgroups (one per half of the query tile).  TILE mode: a thread loads its 64 scores and 64
+//                dP values at once (128 registers), releases the score slot and only then starts the arithmetic    -> 176 regs
+//   warps 12-15  dQ drain warpgroup; its elected lane is also the TMA producer; converts bf16 tiles to fp16      -> 96 regs
+// (r02 also tried FOUR elementwise warpgroups at 768 threads / 80 registers: better MUFU utilisation per unit, 76 % instead of
+// 60 %, but with one score slot the four groups run in lockstep and nothing overlaps the score GEMMs: 2.6 ms instead of 2.25.)
 template <int D, bool BF16>
-__global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = BwdCfg<D>;
   constexpr int SW = Cfg::SW;
   constexpr int NST = Cfg::STAGES;
@@ -241,15 +242,15 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
       mbar_init(&bars->tile_done[i], 3);   // the commits of YV, YK and Z
     }
     for (int i = 0; i < 3; ++i) mbar_init(&bars->s_full[i], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&bars->unit_done[i], 256);  // the two warpgroups that share a unit
+    for (int i = 0; i < 4; ++i) mbar_init(&bars->unit_done[i], 128);
     for (int i = 0; i < 2; ++i) mbar_init(&bars->dq_empty[i], 128);
     mbar_init(&bars->fin_full, 2);         // YV (dV) and YK (dK)
     mbar_init(&bars->kv_ready, 128);
     for (int i = 0; i < 4; ++i) mbar_init(&bars->q_ready[i], 128);
     for (int i = 0; i < 3; ++i) mbar_init(&bars->slot_free[i], 1);
-    mbar_init(&bars->scores_free, 512);
+    mbar_init(&bars->scores_free, 256);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->tile_ready[i], 512);
+      mbar_init(&bars->tile_ready[i], 256);
       mbar_init(&bars->p_free[i], 1);
     }
     fence_barrier_init();
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
   const float ds_scale = ds_scale_from_amax(__ldg(p.dout_amax_bits));  // 2^-e
 
   if (warp < 4) {
-    reg_dealloc<56>();
+    reg_dealloc<64>();
     // ---------------- MMA issuers ----------------
     // Work is pipelined in "units" u = 2 i + h: half h (64 query rows) of query tile i.  Unit u's scores live in TMEM
     // slot u % NSLOT; warpgroup h turns them into P^T (fp16, over the front of the slot) and the dS^T box (pair i & 1,
@@ -388,9 +389,8 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
         if (leader) {
           HSTU_TSTAMP(1, u, 1);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half; P^T of query chunk c sits at columns [32 c, 32 c + 16)
-            mma_ts(tmem + Cfg::TMEM_DV, tp + (ks >> 1) * 32 + (ks & 1) * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv,
-                   (u > 0) || (ks > 0));
+          for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
+            mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (u > 0) || (ks > 0));
           mma_commit(&bars->slot_free[slot]);                // the score issuer may overwrite the slot
           if (hf == 1) mma_commit(&bars->tile_done[i & 3]);  // this issuer is done with dO_i
           HSTU_TSTAMP(1, u, 2);
@@ -471,8 +471,8 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
         __syncwarp();
       }
     }
-  } else if (warp >= 20) {
-    reg_alloc<96>();  // paid for by the issuer warps: the pool of a CTA is what it was launched with (768 x 80 registers)
+  } else if (warp >= 12) {
+    reg_dealloc<96>();
     // ---------------- dQ drain warpgroup (+ TMA producer on its elected lane) ----------------
     // dQ tile of query tile i: TMEM (lane = query row) -> swizzled fp32 staging box (32 columns) in shared memory -> ONE TMA
     // reduce-add per box into dq_acc.  Two staging boxes alternate, so a reduce may still be reading one while the next is being
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
     const int quad = warp & 3;
     const int row = quad * 32 + lane;              // query row inside the tile == TMEM lane
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
-    const bool elected = warp == 20 && lane == 0;
+    const bool elected = warp == 12 && lane == 0;
     auto load_tile = [&](int i) {
       const int st = i % NST;
       mbar_arrive_expect_tx(&bars->q_full[st], 2 * Cfg::TILE_BYTES);
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
       }
       for (int i = 0; i < NST && i < T; ++i) load_tile(i);
     }
-    const int ct = tid - 640;  // index inside this warpgroup
+    const int ct = tid - 384;  // index inside this warpgroup
     auto convert_tile = [&](int i) {  // Q_i (as is) and dO_i (times 2^-e) of stage i % NST: bf16 -> fp16 in place
       const int st = i % NST;
       mbar_wait(&bars->q_full[st], (i / NST) & 1);
@@ -558,11 +558,9 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
     }
     if (elected) bulk_wait_group_read0();          // shared memory must stay valid until the last reduce has read it
   } else {
-    // (stays at the 80 registers of the launch: 4 x 128 x 80 + 128 x 56 + 128 x 96 = 768 x 80, the whole pool of the CTA)
+    reg_alloc<176>();
     // ---------------- elementwise warpgroups ----------------
-    const int wg = (warp - 4) >> 2;                // 0..3
-    const int hf = wg >> 1;                        // half of the query tile = which units (u = 2 i + hf)
-    const int cc = wg & 1;                         // 32-column chunk of the unit's 64 query columns
+    const int wg = (warp - 4) >> 2;                // owns query columns [64*wg, 64*wg + 64) of every tile
     const int quad = warp & 3;
     const int row = quad * 32 + lane;              // key row inside the tile == TMEM lane
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
@@ -576,122 +574,138 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
     const bool fast = msk.fast != 0;
     const bool j_ok = j_pos < len;
     const bool j_hist = j_ok && (!msk.has_tgt || j_pos < msk.max_id);  // fast mask: valid = (j_hist & i > j) | (i == j)
-    const int cbase = hf * 64;
-    const bool stamp = cc == 0 && quad == 0 && lane == 0;
+    const int cbase = wg * 64;
+    const bool stamp = quad == 0 && lane == 0;
+
+    // p = x sig(x) and g = sig (1 + x (1 - sig)) from one tanh: x = 2 hh, sig = (1 + t) / 2
+    // packed fp32x2 arithmetic (FMUL2 / FFMA2): two elements per issued instruction, one MUFU.TANH per element
+#define HSTU_BWD_ELEM2(S0, S1, DP0, DP1, P0, P1, D0, D1)                                                       \
+  {                                                                                                            \
+    const float2 hh = __fmul2_rn(make_float2(__uint_as_float(S0), __uint_as_float(S1)), ah2);                  \
+    const float2 t = make_float2(tanh_approx(hh.x), tanh_approx(hh.y));                                        \
+    const float2 pv = __ffma2_rn(hh, t, hh);                                                                   \
+    const float2 sig = __ffma2_rn(shalf2v, t, shalf2v);   /* scale * sig        */                             \
+    const float2 onem = __ffma2_rn(nshalf2v, t, shalf2v); /* scale * (1 - sig)  */                             \
+    const float2 dv = __fmul2_rn(make_float2(__uint_as_float(DP0), __uint_as_float(DP1)),                      \
+                                 __ffma2_rn(pv, onem, sig));                                                   \
+    P0 = pv.x; P1 = pv.y; D0 = dv.x; D1 = dv.y;                                                                \
+  }
+    // 16 consecutive query columns starting at column `col0` of this half: scores sv / dpv -> packed fp16 P^T (pp) and dS^T (dd)
+#define HSTU_BWD_CHUNK16(SV, DPV, OFF, col0)                                                                   \
+  if (mode == 0) {                                                                                             \
+    _Pragma("unroll") for (int e = 0; e < 16; e += 2) {                                                        \
+      float p0, p1, d0, d1;                                                                                    \
+      HSTU_BWD_ELEM2(SV[OFF + e], SV[OFF + e + 1], DPV[OFF + e], DPV[OFF + e + 1], p0, p1, d0, d1);            \
+      pp[e >> 1] = pack_f16x2_sat(p0, p1);                                                                     \
+      dd[e >> 1] = pack_f16x2_sat(d0, d1);                                                                     \
+    }                                                                                                          \
+  } else if (mode == 1) {                                                                                      \
+    /* valid(i, j) = ((j is history) & (i > j)) | (i == j), restricted to i < len and j < len */               \
+    const int lo_c = j_hist ? jr : 0x7fffffff;       /* columns > lo_c are valid (if j is a history position) */ \
+    const int dg_c = j_ok ? jr : -0x7fffffff;        /* the diagonal column */                                 \
+    _Pragma("unroll") for (int e = 0; e < 16; e += 2) {                                                        \
+      float p0, p1, d0, d1;                                                                                    \
+      HSTU_BWD_ELEM2(SV[OFF + e], SV[OFF + e + 1], DPV[OFF + e], DPV[OFF + e + 1], p0, p1, d0, d1);            \
+      const int c0 = (col0) + e;                                                                               \
+      const bool v0 = ((c0 > lo_c) | (c0 == dg_c)) & (c0 < len_rel);                                           \
+      const bool v1 = ((c0 + 1 > lo_c) | (c0 + 1 == dg_c)) & (c0 + 1 < len_rel);                               \
+      p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;                                                                  \
+      p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;                                                                  \
+      pp[e >> 1] = pack_f16x2_sat(p0, p1);                                                                     \
+      dd[e >> 1] = pack_f16x2_sat(d0, d1);                                                                     \
+    }                                                                                                          \
+  } else {                                                                                                     \
+    _Pragma("unroll") for (int e = 0; e < 16; e += 2) {                                                        \
+      float p0, p1, d0, d1;                                                                                    \
+      HSTU_BWD_ELEM2(SV[OFF + e], SV[OFF + e + 1], DPV[OFF + e], DPV[OFF + e + 1], p0, p1, d0, d1);            \
+      const int i_pos = m0 + cbase + (col0) + e;                                                               \
+      const bool v0 = j_ok && i_pos < len && mask_valid(msk, i_pos, j_pos);                                    \
+      const bool v1 = j_ok && i_pos + 1 < len && mask_valid(msk, i_pos + 1, j_pos);                            \
+      p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;                                                                  \
+      p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;                                                                  \
+      pp[e >> 1] = pack_f16x2_sat(p0, p1);                                                                     \
+      dd[e >> 1] = pack_f16x2_sat(d0, d1);                                                                     \
+    }                                                                                                          \
+  }
 
     for (int i = 0; i < T; ++i) {
-      const int u = 2 * i + hf, slot = u % Cfg::NSLOT;
+      const int u = 2 * i + wg, slot = u % Cfg::NSLOT;
       const int m0 = q_tile(i) * 128;
-      if (stamp) HSTU_TSTAMP(2 + hf, i, 0);
+      if (stamp) HSTU_TSTAMP(2 + wg, i, 0);
       if (Cfg::TILE) mbar_wait(&bars->s_full[0], i & 1);
       else mbar_wait(&bars->s_full[u % Cfg::NSF], (u / Cfg::NSF) & 1);
       tc_fence_after_sync();
-      if (stamp) HSTU_TSTAMP(2 + hf, i, 1);
-      // classification of this half-tile (uniform over the two warpgroups of the unit)
+      if (stamp) HSTU_TSTAMP(2 + wg, i, 1);
+      // classification of this half-tile (uniform over the warpgroup)
       const int mh0 = m0 + cbase;                   // first query row of the half
       const bool full = fast && (mh0 >= n0 + 128) && (mh0 + 64 <= len) && (!msk.has_tgt || n0 + 128 <= msk.max_id);
       const int mode = full ? 0 : (fast ? 1 : 2);
-      const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + hf * 16384);
-      const int jr = j_pos - m0 - cbase;           // query column (relative to the half) equal to j
+      const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + wg * 16384);
+      const int jr = j_pos - m0 - cbase;           // query column (relative to this warpgroup's half) equal to j
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
       // TILE mode: the score slot holds the whole tile (this half starts at column cbase of S^T and of dP^T); unit mode: the
       // slot holds one half-tile {S^T | dP^T}
       const uint32_t st_addr = tmem + (Cfg::TILE ? Cfg::TMEM_S + cbase : Cfg::TMEM_SLOT + slot * 128) + lane_bits;
       const uint32_t dp_addr = tmem + (Cfg::TILE ? Cfg::TMEM_DP + cbase : Cfg::TMEM_SLOT + slot * 128 + 64) + lane_bits;
-#pragma unroll
-      for (int sc = 0; sc < 2; ++sc) {  // 2 sub-chunks of 16 query columns
-        const int col0 = cc * 32 + sc * 16;
-        uint32_t s[16], dp[16];
-        tmem_ld16(st_addr + col0, s);
-        tmem_ld16(dp_addr + col0, dp);
+      if (Cfg::TILE) {
+        // all 64 scores and 64 dP values of this thread at once, then the slot is released: the score GEMMs of the next tile
+        // run while this warpgroup does its arithmetic
+        uint32_t s[2][32], dp[2][32];
+        tmem_ld32(st_addr, s[0]);
+        tmem_ld32(st_addr + 32, s[1]);
+        tmem_ld32(dp_addr, dp[0]);
+        tmem_ld32(dp_addr + 32, dp[1]);
         tmem_ld_wait();
-        if (Cfg::TILE && sc == 1) {  // this thread has loaded all of its scores: the issuer may overwrite the slot (tile i + 1)
-          tc_fence_before_sync();
-          mbar_arrive(&bars->scores_free);
+        tc_fence_before_sync();
+        mbar_arrive(&bars->scores_free);
+        if (i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
+        if (i >= Cfg::NP) {
+          mbar_wait(&bars->p_free[i % Cfg::NP], ((i / Cfg::NP) - 1) & 1);           // dV of tile i - NP has consumed the P^T buffer
+          tc_fence_after_sync();
         }
-        uint32_t pp[8], dd[8];
-        // p = x sig(x) and g = sig (1 + x (1 - sig)) from one tanh: x = 2 hh, sig = (1 + t) / 2
-        // packed fp32x2 arithmetic (FMUL2 / FFMA2): two elements per issued instruction, one MUFU.TANH per element
-#define HSTU_BWD_ELEM2(E, P0, P1, D0, D1)                                                                      \
-  {                                                                                                            \
-    const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[E]), __uint_as_float(s[E + 1])), ah2);          \
-    const float2 t = make_float2(tanh_approx(hh.x), tanh_approx(hh.y));                                        \
-    const float2 pv = __ffma2_rn(hh, t, hh);                                                                   \
-    const float2 sig = __ffma2_rn(shalf2v, t, shalf2v);   /* scale * sig        */                             \
-    const float2 onem = __ffma2_rn(nshalf2v, t, shalf2v); /* scale * (1 - sig)  */                             \
-    const float2 dv = __fmul2_rn(make_float2(__uint_as_float(dp[E]), __uint_as_float(dp[E + 1])),              \
-                                 __ffma2_rn(pv, onem, sig));                                                   \
-    P0 = pv.x; P1 = pv.y; D0 = dv.x; D1 = dv.y;                                                                \
-  }
-        if (mode == 0) {
+        const uint32_t p_addr = tmem + Cfg::TMEM_P + (i % Cfg::NP) * 64 + wg * 32 + lane_bits;
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            float p0, p1, d0, d1;
-            HSTU_BWD_ELEM2(e, p0, p1, d0, d1);
-            pp[e >> 1] = pack_f16x2_sat(p0, p1);
-            dd[e >> 1] = pack_f16x2_sat(d0, d1);
-          }
-        } else if (mode == 1) {
-          // valid(i, j) = ((j is history) & (i > j)) | (i == j), restricted to i < len and j < len
-          const int lo_c = j_hist ? jr : 0x7fffffff;       // columns > lo_c are valid (if j is a history position)
-          const int dg_c = j_ok ? jr : -0x7fffffff;        // the diagonal column
+        for (int c = 0; c < 4; ++c) {  // 4 chunks of 16 query columns
+          uint32_t pp[8], dd[8];
+          HSTU_BWD_CHUNK16(s[c >> 1], dp[c >> 1], (c & 1) * 16, c * 16);
+          tmem_st8(p_addr + c * 8, pp);  // P^T: 16 fp16 = 8 columns of the tile's P^T buffer (A of the dV GEMM)
+          // dS^T [kv][q] (16-byte stores): A of dK as stored, A of dQ read MN-major
+          st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 2), dd[0], dd[1], dd[2], dd[3]);
+          st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 2 + 1), dd[4], dd[5], dd[6], dd[7]);
+        }
+      } else {
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            float p0, p1, d0, d1;
-            HSTU_BWD_ELEM2(e, p0, p1, d0, d1);
-            const int c0 = col0 + e;
-            const bool v0 = ((c0 > lo_c) | (c0 == dg_c)) & (c0 < len_rel);
-            const bool v1 = ((c0 + 1 > lo_c) | (c0 + 1 == dg_c)) & (c0 + 1 < len_rel);
-            p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;
-            p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;
-            pp[e >> 1] = pack_f16x2_sat(p0, p1);
-            dd[e >> 1] = pack_f16x2_sat(d0, d1);
-          }
-        } else {
+        for (int c = 0; c < 2; ++c) {  // 2 chunks of 32 query columns
+          uint32_t s[32], dp[32];
+          tmem_ld32(st_addr + c * 32, s);
+          tmem_ld32(dp_addr + c * 32, dp);
+          tmem_ld_wait();
+          if (c == 0 && i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            float p0, p1, d0, d1;
-            HSTU_BWD_ELEM2(e, p0, p1, d0, d1);
-            const int i_pos = m0 + cbase + col0 + e;
-            const bool v0 = j_ok && i_pos < len && mask_valid(msk, i_pos, j_pos);
-            const bool v1 = j_ok && i_pos + 1 < len && mask_valid(msk, i_pos + 1, j_pos);
-            p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;
-            p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;
-            pp[e >> 1] = pack_f16x2_sat(p0, p1);
-            dd[e >> 1] = pack_f16x2_sat(d0, d1);
+          for (int hc = 0; hc < 2; ++hc) {
+            uint32_t pp[8], dd[8];
+            HSTU_BWD_CHUNK16(s, dp, hc * 16, c * 32 + hc * 16);
+            // P^T (16 fp16 = 8 columns) overwrites the already-read front of the S^T half of the slot: A of the dV GEMM
+            tmem_st8(st_addr + c * 16 + hc * 8, pp);
+            st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + hc * 2), dd[0], dd[1], dd[2], dd[3]);
+            st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + hc * 2 + 1), dd[4], dd[5], dd[6], dd[7]);
           }
         }
-#undef HSTU_BWD_ELEM2
-        if (sc == 0 && i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
-        if (Cfg::TILE) {
-          // P^T has its own ring: buffer i % NP, the 16 fp16 of these query columns at columns [16 wg + 8 sc, + 8)
-          if (sc == 0 && i >= Cfg::NP) {
-            mbar_wait(&bars->p_free[i % Cfg::NP], ((i / Cfg::NP) - 1) & 1);  // dV of tile i - NP has consumed the buffer
-            tc_fence_after_sync();
-          }
-          tmem_st8(tmem + Cfg::TMEM_P + (i % Cfg::NP) * 64 + lane_bits + wg * 16 + sc * 8, pp);
-        } else {
-          // P^T of these 16 query columns (16 fp16 = 8 TMEM columns) goes to columns [32 cc + 8 sc, + 8) of the slot: a part of
-          // THIS warpgroup's S^T region that it has already read (the neighbour warpgroup reads / writes only [32 (1-cc), +32))
-          tmem_st8(st_addr + cc * 32 + sc * 8, pp);
-        }
-        // dS^T [kv][q] (16-byte stores): A of dK as stored, A of dQ read MN-major
-        st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, cc * 4 + sc * 2), dd[0], dd[1], dd[2], dd[3]);
-        st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, cc * 4 + sc * 2 + 1), dd[4], dd[5], dd[6], dd[7]);
       }
       tmem_st_wait();
       tc_fence_before_sync();
       fence_proxy_async_smem();
-      if (stamp) HSTU_TSTAMP(2 + hf, i, 2);
+      if (stamp) HSTU_TSTAMP(2 + wg, i, 2);
       if (Cfg::TILE) mbar_arrive(&bars->tile_ready[i & 1]);
-      else mbar_arrive(&bars->unit_done[hf * 2 + (i & 1)]);
+      else mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);
     }
+#undef HSTU_BWD_CHUNK16
+#undef HSTU_BWD_ELEM2
     // ---------------- epilogue: dV (warpgroup 0) / dK (warpgroup 1): TMEM -> scale -> global ----------------
     mbar_wait(&bars->fin_full, 0);
     tc_fence_after_sync();
-    // warpgroups 0 / 2: the two column halves of dV, warpgroups 1 / 3: of dK
-    const bool is_dv = cc == 0;
-    const int ecol0 = hf * (D / 2);
+    const bool is_dv = wg == 0;
+    const int ecol0 = 0;
     const uint32_t acc = tmem + (is_dv ? Cfg::TMEM_DV : Cfg::TMEM_DK) + ecol0 + lane_bits;
     // undo 2^-e (a power of two: exact): dK always carries it, dV only when dO itself was scaled
     const float scale = is_dv ? (CONV ? p.dv_scale / ds_scale : p.dv_scale) : p.dk_scale / ds_scale;
@@ -699,7 +713,7 @@ __global__ void __launch_bounds__(768, 1) attn_bwd_umma_kernel(const __grid_cons
         ? reinterpret_cast<uint16_t*>(p.dv) + (row0 + j_pos) * p.dv_row_stride + (long long)h * p.dv_head_stride
         : reinterpret_cast<uint16_t*>(p.dk) + (row0 + j_pos) * p.dk_row_stride + (long long)h * p.dk_head_stride) + ecol0;
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < D / 16; ++c) {
       uint32_t o[16];
       tmem_ld16(acc + c * 16, o);
       tmem_ld_wait();
@@ -830,7 +844,7 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   cudaMemset(tbuf, 0, tbytes);
   cudaMemcpyToSymbol(g_trace, &tbuf, sizeof(tbuf));
 #endif
-  kern<<<grid, 768, Cfg::SMEM_BYTES, st>>>(bp);
+  kern<<<grid, 512, Cfg::SMEM_BYTES, st>>>(bp);
   HSTU_CUDA_OK(cudaGetLastError());
 #ifdef HSTU_TRACE
   {

@@ -7,7 +7,7 @@ phases behind (its parity test would then block until the barrier wraps).  Both 
 development (unit_done with a 3-slot ring; s_full with a single slot); this model reproduces them when the fix is removed
 (--break-ud / --break-sf).
 
-Actors: X (scores), YV (dV), YK (dK), Z (dQ) issuers, four elementwise warpgroups W<half><chunk>, D the dQ drain warpgroup whose elected
+Actors: X (scores), YV (dV), YK (dK), Z (dQ) issuers, two elementwise warpgroups W0 / W1, D the dQ drain warpgroup whose elected
 lane is also the TMA producer.  tcgen05.commit and TMA completions are asynchronous: they are queued per issuing actor and
 fire later, in order.
 usage: sim_bwd_protocol.py [--d 32|64|128] [--tiles T] [--seeds N] [--break-ud] [--break-sf]"""
@@ -39,11 +39,11 @@ def run_tile(T, d, seed):
     NST = {32: 4, 64: 3}[d]
     NP = NDQ = {32: 2, 64: 1}[d]
     rnd = random.Random(seed)
-    B = {"kv": Bar(1), "kvr": Bar(1), "fin": Bar(2), "sf": Bar(1), "free": Bar(4)}
+    B = {"kv": Bar(1), "kvr": Bar(1), "fin": Bar(2), "sf": Bar(1), "free": Bar(2)}
     for i in range(4):
         B[f"qf{i}"], B[f"qr{i}"], B[f"td{i}"] = Bar(1), Bar(1), Bar(3)
     for i in range(2):
-        B[f"tr{i}"], B[f"pf{i}"], B[f"dqe{i}"] = Bar(4), Bar(1), Bar(1)
+        B[f"tr{i}"], B[f"pf{i}"], B[f"dqe{i}"] = Bar(2), Bar(1), Bar(1)
 
     def X():
         yield ("wait", "kvr", 0)
@@ -77,12 +77,11 @@ def run_tile(T, d, seed):
     def W():
         for i in range(T):
             yield ("wait", "sf", i)
-            # sub-chunk 0: load, compute, then the stores wait for the dS^T box pair and the P^T buffer
+            yield ("arrive", "free")        # all scores loaded: the score slot may be overwritten
             if i >= 2:
                 yield ("wait", f"td{(i - 2) & 3}", (i - 2) >> 2)
             if i >= NP:
                 yield ("wait", f"pf{i % NP}", i // NP - 1)
-            yield ("arrive", "free")        # sub-chunk 1 loaded: the score slot may be overwritten
             yield ("arrive", f"tr{i & 1}")
         yield ("wait", "fin", 0)
 
@@ -104,7 +103,7 @@ def run_tile(T, d, seed):
                 yield ("wait", f"qf{(i + NST) % NST}", (i + NST) // NST)
                 yield ("arrive", f"qr{(i + NST) % NST}")
 
-    actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W0": W(), "W1": W(), "W2": W(), "W3": W(), "D": Dr()}
+    actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W0": W(), "W1": W(), "D": Dr()}
     return _simulate(actors, B, rnd)
 
 
@@ -169,7 +168,7 @@ def run(T, d, seed, break_ud=False, break_sf=False):
         B[f"qf{i}"] = Bar(1)
         B[f"qr{i}"] = Bar(1)       # bf16 inputs: tile converted to fp16 (128 drain threads modelled as one arrival)
         B[f"td{i}"] = Bar(3)       # YV, YK, Z
-        B[f"ud{i}"] = Bar(2)       # the two warpgroups that share a unit (128 threads modelled as one arrival each)
+        B[f"ud{i}"] = Bar(1)       # count 128 threads modelled as one arrival per warpgroup
     for i in range(3):
         B[f"sf{i}"] = Bar(1)
         B[f"free{i}"] = Bar(1)
@@ -246,8 +245,7 @@ def run(T, d, seed, break_ud=False, break_sf=False):
                 yield ("wait", f"qf{(i + NST) % NST}", (i + NST) // NST)
                 yield ("arrive", f"qr{(i + NST) % NST}")
 
-    # four elementwise warpgroups: (half 0, chunk 0/1), (half 1, chunk 0/1)
-    actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W00": W(0), "W01": W(0), "W10": W(1), "W11": W(1), "D": Dr()}
+    actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W0": W(0), "W1": W(1), "D": Dr()}
     pending = {k: None for k in actors}     # the blocking wait of each actor
     queues = {k: [] for k in actors}        # asynchronous completions (commit / TMA), in order per actor
     done = set()
