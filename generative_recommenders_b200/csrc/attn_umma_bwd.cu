@@ -84,7 +84,7 @@ struct BwdCfg {
   //
   // TILE mode (d <= 64), r02: the half-tile units above made the issuer of the scores wait for the dV GEMM of three units
   // earlier (the slot holds P^T until then): a dependency cycle X -> elementwise -> YV -> X of ~3700 clk per three units that
-  // set the pace of the whole CTA (profiles/r02_bwd_timeline_units.txt).  In TILE mode there is ONE score slot for a whole query
+  // set the pace of the whole CTA (profiles/r02_bwd_timelines.txt).  In TILE mode there is ONE score slot for a whole query
   // tile {S^T: 128 columns | dP^T: 128 columns}, written by N = 128 MMAs (64 clk each instead of 2 x 48 for two N = 64 halves),
   // and P^T goes to its own small ring (NP buffers of 64 columns): the slot is free again as soon as the four elementwise
   // warpgroups have LOADED it (scores_free), half way through their work, not after the dV GEMM.  d = 128 keeps the units: its
@@ -590,41 +590,44 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
                                  __ffma2_rn(pv, onem, sig));                                                   \
     P0 = pv.x; P1 = pv.y; D0 = dv.x; D1 = dv.y;                                                                \
   }
-    // 16 consecutive query columns starting at column `col0` of this half: scores sv / dpv -> packed fp16 P^T (pp) and dS^T (dd)
-#define HSTU_BWD_CHUNK16(SV, DPV, OFF, col0)                                                                   \
+    // NE consecutive query columns starting at column `col0` of this half: scores / dP (SREF(e), DREF(e) = element e of the run)
+    // -> packed fp16 P^T (PP[e / 2]) and dS^T (DD[e / 2]).  ONE block of straight-line code per mask mode: the tile-uniform branch
+    // sits outside, so the scheduler can interleave all NE / 2 independent MUFU -> FFMA2 chains (r02: with the branch and the
+    // stores inside 16-column chunks every chunk exposed its own latency: 2750 clk per tile instead of 1700).
+#define HSTU_BWD_RUN(NE, SREF, DREF, PP, DD, col0)                                                             \
   if (mode == 0) {                                                                                             \
-    _Pragma("unroll") for (int e = 0; e < 16; e += 2) {                                                        \
+    _Pragma("unroll") for (int e = 0; e < NE; e += 2) {                                                        \
       float p0, p1, d0, d1;                                                                                    \
-      HSTU_BWD_ELEM2(SV[OFF + e], SV[OFF + e + 1], DPV[OFF + e], DPV[OFF + e + 1], p0, p1, d0, d1);            \
-      pp[e >> 1] = pack_f16x2_sat(p0, p1);                                                                     \
-      dd[e >> 1] = pack_f16x2_sat(d0, d1);                                                                     \
+      HSTU_BWD_ELEM2(SREF(e), SREF(e + 1), DREF(e), DREF(e + 1), p0, p1, d0, d1);                              \
+      PP[e >> 1] = pack_f16x2_sat(p0, p1);                                                                     \
+      DD[e >> 1] = pack_f16x2_sat(d0, d1);                                                                     \
     }                                                                                                          \
   } else if (mode == 1) {                                                                                      \
     /* valid(i, j) = ((j is history) & (i > j)) | (i == j), restricted to i < len and j < len */               \
     const int lo_c = j_hist ? jr : 0x7fffffff;       /* columns > lo_c are valid (if j is a history position) */ \
     const int dg_c = j_ok ? jr : -0x7fffffff;        /* the diagonal column */                                 \
-    _Pragma("unroll") for (int e = 0; e < 16; e += 2) {                                                        \
+    _Pragma("unroll") for (int e = 0; e < NE; e += 2) {                                                        \
       float p0, p1, d0, d1;                                                                                    \
-      HSTU_BWD_ELEM2(SV[OFF + e], SV[OFF + e + 1], DPV[OFF + e], DPV[OFF + e + 1], p0, p1, d0, d1);            \
+      HSTU_BWD_ELEM2(SREF(e), SREF(e + 1), DREF(e), DREF(e + 1), p0, p1, d0, d1);                              \
       const int c0 = (col0) + e;                                                                               \
       const bool v0 = ((c0 > lo_c) | (c0 == dg_c)) & (c0 < len_rel);                                           \
       const bool v1 = ((c0 + 1 > lo_c) | (c0 + 1 == dg_c)) & (c0 + 1 < len_rel);                               \
       p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;                                                                  \
       p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;                                                                  \
-      pp[e >> 1] = pack_f16x2_sat(p0, p1);                                                                     \
-      dd[e >> 1] = pack_f16x2_sat(d0, d1);                                                                     \
+      PP[e >> 1] = pack_f16x2_sat(p0, p1);                                                                     \
+      DD[e >> 1] = pack_f16x2_sat(d0, d1);                                                                     \
     }                                                                                                          \
   } else {                                                                                                     \
-    _Pragma("unroll") for (int e = 0; e < 16; e += 2) {                                                        \
+    _Pragma("unroll") for (int e = 0; e < NE; e += 2) {                                                        \
       float p0, p1, d0, d1;                                                                                    \
-      HSTU_BWD_ELEM2(SV[OFF + e], SV[OFF + e + 1], DPV[OFF + e], DPV[OFF + e + 1], p0, p1, d0, d1);            \
+      HSTU_BWD_ELEM2(SREF(e), SREF(e + 1), DREF(e), DREF(e + 1), p0, p1, d0, d1);                              \
       const int i_pos = m0 + cbase + (col0) + e;                                                               \
       const bool v0 = j_ok && i_pos < len && mask_valid(msk, i_pos, j_pos);                                    \
       const bool v1 = j_ok && i_pos + 1 < len && mask_valid(msk, i_pos + 1, j_pos);                            \
       p0 = v0 ? p0 : 0.f; d0 = v0 ? d0 : 0.f;                                                                  \
       p1 = v1 ? p1 : 0.f; d1 = v1 ? d1 : 0.f;                                                                  \
-      pp[e >> 1] = pack_f16x2_sat(p0, p1);                                                                     \
-      dd[e >> 1] = pack_f16x2_sat(d0, d1);                                                                     \
+      PP[e >> 1] = pack_f16x2_sat(p0, p1);                                                                     \
+      DD[e >> 1] = pack_f16x2_sat(d0, d1);                                                                     \
     }                                                                                                          \
   }
 
@@ -658,21 +661,33 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         tmem_ld_wait();
         tc_fence_before_sync();
         mbar_arrive(&bars->scores_free);
+        uint32_t pp[32], dd[32];
+#define HSTU_S64(e) s[(e) >> 5][(e) & 31]
+#define HSTU_D64(e) dp[(e) >> 5][(e) & 31]
+        HSTU_BWD_RUN(64, HSTU_S64, HSTU_D64, pp, dd, 0);
+#undef HSTU_S64
+#undef HSTU_D64
         if (i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
         if (i >= Cfg::NP) {
           mbar_wait(&bars->p_free[i % Cfg::NP], ((i / Cfg::NP) - 1) & 1);           // dV of tile i - NP has consumed the P^T buffer
           tc_fence_after_sync();
         }
+        // P^T: 64 fp16 = 32 columns of the tile's P^T buffer (A of the dV GEMM)
         const uint32_t p_addr = tmem + Cfg::TMEM_P + (i % Cfg::NP) * 64 + wg * 32 + lane_bits;
+        {
+          uint32_t lo[16], hi[16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {  // 4 chunks of 16 query columns
-          uint32_t pp[8], dd[8];
-          HSTU_BWD_CHUNK16(s[c >> 1], dp[c >> 1], (c & 1) * 16, c * 16);
-          tmem_st8(p_addr + c * 8, pp);  // P^T: 16 fp16 = 8 columns of the tile's P^T buffer (A of the dV GEMM)
-          // dS^T [kv][q] (16-byte stores): A of dK as stored, A of dQ read MN-major
-          st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 2), dd[0], dd[1], dd[2], dd[3]);
-          st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 2 + 1), dd[4], dd[5], dd[6], dd[7]);
+          for (int e = 0; e < 16; ++e) {
+            lo[e] = pp[e];
+            hi[e] = pp[16 + e];
+          }
+          tmem_st16(p_addr, lo);
+          tmem_st16(p_addr + 16, hi);
         }
+        // dS^T [kv][q] (16-byte stores): A of dK as stored, A of dQ read MN-major
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c), dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
       } else {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {  // 2 chunks of 32 query columns
@@ -681,15 +696,17 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
           tmem_ld32(dp_addr + c * 32, dp);
           tmem_ld_wait();
           if (c == 0 && i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
+          uint32_t pp[16], dd[16];
+#define HSTU_S32(e) s[e]
+#define HSTU_D32(e) dp[e]
+          HSTU_BWD_RUN(32, HSTU_S32, HSTU_D32, pp, dd, c * 32);
+#undef HSTU_S32
+#undef HSTU_D32
+          // P^T chunk c (32 fp16 = 16 columns) overwrites the already-read front of the S^T half of the slot: A of the dV GEMM
+          tmem_st16(st_addr + c * 16, pp);
 #pragma unroll
-          for (int hc = 0; hc < 2; ++hc) {
-            uint32_t pp[8], dd[8];
-            HSTU_BWD_CHUNK16(s, dp, hc * 16, c * 32 + hc * 16);
-            // P^T (16 fp16 = 8 columns) overwrites the already-read front of the S^T half of the slot: A of the dV GEMM
-            tmem_st8(st_addr + c * 16 + hc * 8, pp);
-            st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + hc * 2), dd[0], dd[1], dd[2], dd[3]);
-            st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + hc * 2 + 1), dd[4], dd[5], dd[6], dd[7]);
-          }
+          for (int j4 = 0; j4 < 4; ++j4)
+            st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + j4), dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
         }
       }
       tmem_st_wait();
@@ -699,7 +716,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       if (Cfg::TILE) mbar_arrive(&bars->tile_ready[i & 1]);
       else mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);
     }
-#undef HSTU_BWD_CHUNK16
+#undef HSTU_BWD_RUN
 #undef HSTU_BWD_ELEM2
     // ---------------- epilogue: dV (warpgroup 0) / dK (warpgroup 1): TMEM -> scale -> global ----------------
     mbar_wait(&bars->fin_full, 0);
