@@ -182,6 +182,22 @@ __global__ void mufu_bench_kernel(float* out, int iters) {
       asm("ex2.approx.f16x2 %0, %0;" : "+r"(pa)); asm("ex2.approx.f16x2 %0, %0;" : "+r"(pb));
     } else if (MODE == 5) {  // FMA pipe reference: 4 independent FFMA chains
       a = fmaf(a, 1.0001f, 0.5f); b = fmaf(b, 1.0001f, 0.5f); c = fmaf(c, 1.0001f, 0.5f); d = fmaf(d, 1.0001f, 0.5f);
+    } else if (MODE == 6) {  // pack two fp32 into bf16x2 (the result is fed back through a cheap integer op to keep a chain)
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pa) : "f"(a), "f"(b)); a = __uint_as_float(pa | 0x3f000000u);
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pb) : "f"(c), "f"(d)); c = __uint_as_float(pb | 0x3f000000u);
+    } else if (MODE == 7) {  // pack two fp32 into f16x2
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pa) : "f"(a), "f"(b)); a = __uint_as_float(pa | 0x3f000000u);
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pb) : "f"(c), "f"(d)); c = __uint_as_float(pb | 0x3f000000u);
+    } else if (MODE == 8) {  // saturating form
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pa) : "f"(a), "f"(b)); a = __uint_as_float(pa | 0x3f000000u);
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pb) : "f"(c), "f"(d)); c = __uint_as_float(pb | 0x3f000000u);
+    } else if (MODE == 9) {  // packed half2 FMA
+      asm("fma.rn.f16x2 %0, %0, %1, %1;" : "+r"(pa) : "r"(pb)); asm("fma.rn.f16x2 %0, %0, %1, %1;" : "+r"(pb) : "r"(pa));
+    } else if (MODE == 10) {  // bf16x2 -> two fp32 by shifts, times a scale, -> f16x2 (the in-place operand conversion)
+      const float lo = __uint_as_float(pa << 16) * 0.5f, hi = __uint_as_float(pa & 0xffff0000u) * 0.5f;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pa) : "f"(hi), "f"(lo));
+      const float lo2 = __uint_as_float(pb << 16) * 0.5f, hi2 = __uint_as_float(pb & 0xffff0000u) * 0.5f;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pb) : "f"(hi2), "f"(lo2));
     }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = a + b + c + d + __uint_as_float(pa) + __uint_as_float(pb);
@@ -592,6 +608,12 @@ int umma_selftest(char* report, size_t cap) {
   mufu_case<3>("tanh.approx.f16x2", 4, report, cap);
   mufu_case<4>("ex2.approx.f16x2", 4, report, cap);
   mufu_case<5>("ffma f32 (reference)", 4, report, cap);
+  // packing conversions: which pipe / rate?  (per_iter counts PACK INSTRUCTIONS, two fp32 -> one 32-bit register each)
+  mufu_case<6>("cvt.rn.bf16x2.f32 (packs)", 2, report, cap);
+  mufu_case<7>("cvt.rn.f16x2.f32 (packs)", 2, report, cap);
+  mufu_case<8>("cvt.rn.satfinite.f16x2.f32", 2, report, cap);
+  mufu_case<9>("fma.rn.f16x2 (instr)", 2, report, cap);
+  mufu_case<10>("bf16x2 -> f16x2 via fp32", 2, report, cap);
   rep(report, cap, "failed checks: %d\n", fails);
   return fails;
 }
