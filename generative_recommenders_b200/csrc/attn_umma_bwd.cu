@@ -82,31 +82,33 @@ struct BwdCfg {
   // dK accumulators and NDQ dQ accumulators (tile i -> buffer i % NDQ; with two, the warpgroups drain dQ two tiles late and
   // never wait for it).  d = 128 fills TMEM with one slot and one dQ accumulator: 128 + 3 * 128 columns.
   //
-  // TILE mode (d <= 64), r02: the half-tile units above made the issuer of the scores wait for the dV GEMM of three units
-  // earlier (the slot holds P^T until then): a dependency cycle X -> elementwise -> YV -> X of ~3700 clk per three units that
-  // set the pace of the whole CTA (profiles/r02_bwd_timelines.txt).  In TILE mode there is ONE score slot for a whole query
-  // tile {S^T: 128 columns | dP^T: 128 columns}, written by N = 128 MMAs (64 clk each instead of 2 x 48 for two N = 64 halves),
-  // and P^T goes to its own small ring (NP buffers of 64 columns): the slot is free again as soon as the four elementwise
-  // warpgroups have LOADED it (scores_free), half way through their work, not after the dV GEMM.  d = 128 keeps the units: its
-  // dK / dV accumulators leave no room for a second tensor of scores.
-  static constexpr bool TILE = D <= 64;
-  static constexpr int NSLOT = TILE ? 2 : 1;     // unit mode: score slots of 128 columns (TILE mode: the one 256-column slot)
-  static constexpr int NP = (D <= 32) ? 2 : 1;   // TILE mode: P^T buffers (tile i -> i % NP)
+  // PRING mode (d <= 64), r02.  In r01 the slot of a unit also carried its P^T (written over the scores), so the issuer of the
+  // scores had to wait for the dV GEMM of the unit three back: a dependency cycle X -> elementwise -> YV -> X of ~3700 clk per
+  // three units that set the pace of the CTA (profiles/r02_bwd_timelines.txt (A)).  Now P^T goes to its own small ring of NPR
+  // buffers (32 columns each) and a warpgroup loads ALL its scores (64 + 64 registers) before it starts the arithmetic: each
+  // warpgroup owns one slot (unit u -> slot u & 1) and hands it back (scores_free) right after the load, so the scores of its
+  // next unit are computed while it works.  The two warpgroups stay half a unit apart by themselves, which keeps the MUFU / pack
+  // pipe busy through each other's load / store phases.  (A whole-tile variant with one 256-column slot and N = 128 score MMAs,
+  // (C) / (D) in the same file, has 28 % less tensor-pipe work but forces both warpgroups into lockstep: 2.8 ms instead of 2.25.)
+  // d = 128 keeps the r01 layout: its dK / dV accumulators leave room for one slot only and none for a P^T ring.
+  static constexpr bool PRING = D <= 64;
+  static constexpr int NSLOT = PRING ? 2 : 1;
+  static constexpr int NPR = (D <= 32) ? 4 : 2;  // PRING: P^T buffers (unit u -> u % NPR)
   static constexpr int NDQ = (D <= 32) ? 2 : 1;
   // s_full barrier instances: unit u -> [u % NSF].  At least two even with one slot: the warpgroups alternate units, and a
   // warpgroup must never wait for phase k+1 of a barrier before phase k has completed (the parity test would pass at once).
   static constexpr int NSF = NSLOT < 2 ? 2 : NSLOT;
   static constexpr int LAG = NDQ;                // the warpgroups drain dQ of tile i - LAG after their unit of tile i
   static constexpr int TMEM_SLOT = 0;
-  static constexpr int TMEM_S = 0, TMEM_DP = 128, TMEM_P = 256;  // TILE mode
-  static constexpr int TMEM_DV = TILE ? 256 + NP * 64 : NSLOT * 128;
+  static constexpr int TMEM_P = NSLOT * 128;     // PRING: NPR buffers of 32 columns
+  static constexpr int TMEM_DV = NSLOT * 128 + (PRING ? NPR * 32 : 0);
   static constexpr int TMEM_DK = TMEM_DV + D;
   static constexpr int TMEM_DQ = TMEM_DK + D;   // NDQ buffers of D columns
   static_assert(TMEM_DQ + NDQ * D <= 512, "TMEM budget");
   // scripts/sim_bwd_protocol.py: a 3-slot score ring needs the Q/dO ring to be at least 4 deep (the scores of tile i+2 are
   // requested before tile i releases its stage), otherwise the producer and the MMA issuer wait on each other.
   static_assert(NSLOT != 3 || STAGES >= 4, "3-slot score ring needs >= 4 Q/dO stages");
-  static_assert(!TILE || STAGES >= 3, "TILE mode: tile i + 1 is staged while tile i is in flight and tile i - 1 drains");
+  static_assert(!PRING || STAGES >= 3, "PRING: tile i + 1 is staged while tile i is in flight and tile i - 1 drains");
 };
 
 struct BwdBars {
@@ -117,9 +119,9 @@ struct BwdBars {
   uint64_t tile_done[4];  // tile i -> [i % 4]: both issuers have finished every GEMM of query tile i (count 2)
   uint64_t slot_free[3];  // unit u -> [u % NSLOT]: dV of the unit has consumed P^T in the slot
   uint64_t dq_empty[2], fin_full;
-  // TILE mode: scores_free (2 x 128 arrivals: every elementwise thread has loaded its part of the score slot),
-  // tile_ready[i & 1] (2 x 128: P^T and dS^T of tile i are written), p_free[i % NP] (YV: dV of the tile has consumed P^T)
-  uint64_t scores_free, tile_ready[2], p_free[2];
+  // PRING: scores_free[h] (128 arrivals: warpgroup h has loaded the scores of its unit), p_free[u % NPR] (YV: dV of the unit has
+  // consumed the P^T buffer)
+  uint64_t scores_free[2], p_free[4];
   uint32_t tmem_base;
 };
 
@@ -186,8 +188,8 @@ __device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async
 // 512 threads = 4 warpgroups with their own register budgets (setmaxnreg; 128 regs / thread at launch -- a CTA can only
 // redistribute the pool it was launched with: requests beyond it spin forever in setmaxnreg.inc):
 //   warps 0-3    issuers X (scores), YV (dV), YK (dK), Z (dQ): one elected lane each                          -> 64 regs
-//   warps 4-11   two elementwise warpgroups (one per half of the query tile).  TILE mode: a thread loads its 64 scores and 64
-//                dP values at once (128 registers), releases the score slot and only then starts the arithmetic    -> 176 regs
+//   warps 4-11   two elementwise warpgroups (one per half of the query tile).  PRING mode: a thread loads its 64 scores and 64
+//                dP values at once (128 registers), hands the score slot back and only then starts the arithmetic  -> 176 regs
 //   warps 12-15  dQ drain warpgroup; its elected lane is also the TMA producer; converts bf16 tiles to fp16      -> 96 regs
 // (r02 also tried FOUR elementwise warpgroups at 768 threads / 80 registers: better MUFU utilisation per unit, 76 % instead of
 // 60 %, but with one score slot the four groups run in lockstep and nothing overlaps the score GEMMs: 2.6 ms instead of 2.25.)
@@ -248,11 +250,8 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     mbar_init(&bars->kv_ready, 128);
     for (int i = 0; i < 4; ++i) mbar_init(&bars->q_ready[i], 128);
     for (int i = 0; i < 3; ++i) mbar_init(&bars->slot_free[i], 1);
-    mbar_init(&bars->scores_free, 256);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->tile_ready[i], 256);
-      mbar_init(&bars->p_free[i], 1);
-    }
+    for (int i = 0; i < 2; ++i) mbar_init(&bars->scores_free[i], 128);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars->p_free[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
@@ -286,43 +285,15 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       const uint64_t ddo_k = desc_kmajor<SW>(smem_u32(sDO), 0);                      // dO_i rows as K-major B
       mbar_wait(kv_rdy, 0);
       tc_fence_after_sync();
-      if (Cfg::TILE) {
-        // one score slot per query tile, N = 128: S^T = K Q_i^T into columns [0, 128), dP^T = V dO_i^T into [128, 256)
-        constexpr uint32_t idesc_t = make_idesc(128, 128, false, false, false, false);
-        for (int i = 0; i < T; ++i) {
-          const int st = i % NST;
-          if (leader) HSTU_TSTAMP(0, i, 0);
-          if (i >= 1) {  // every elementwise thread has loaded its part of the scores of tile i - 1
-            mbar_wait(&bars->scores_free, (i - 1) & 1);
-            tc_fence_after_sync();
-          }
-          mbar_wait(&q_rdy[st], (i / NST) & 1);
-          tc_fence_after_sync();
-          const uint64_t tile_off = (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
-          if (leader) {
-            HSTU_TSTAMP(0, i, 1);
-#pragma unroll
-            for (int ks = 0; ks < D / 16; ++ks) {
-              const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
-              const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
-              mma_ss(tmem + Cfg::TMEM_S, dk_k + o, dq_k + tile_off + o, idesc_t, ks > 0);
-            }
-#pragma unroll
-            for (int ks = 0; ks < D / 16; ++ks) {
-              const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
-              const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
-              mma_ss(tmem + Cfg::TMEM_DP, dv_k + o, ddo_k + tile_off + o, idesc_t, ks > 0);
-            }
-            mma_commit(&bars->s_full[0]);
-            HSTU_TSTAMP(0, i, 2);
-          }
-          __syncwarp();
-        }
-      } else
       for (int u = 0; u < U; ++u) {
         const int i = u >> 1, hf = u & 1, st = i % NST, slot = u % NSLOT;
         if (leader) HSTU_TSTAMP(0, u, 0);
-        if (u >= NSLOT) {  // the slot still holds P^T of unit u - NSLOT until its dV GEMM has completed
+        if (Cfg::PRING) {
+          if (i >= 1) {  // warpgroup hf has loaded the scores of its previous unit out of this slot
+            mbar_wait(&bars->scores_free[hf], (i - 1) & 1);
+            tc_fence_after_sync();
+          }
+        } else if (u >= NSLOT) {  // the slot still holds P^T of unit u - NSLOT until its dV GEMM has completed
           mbar_wait(&bars->slot_free[slot], (u / NSLOT - 1) & 1);
           tc_fence_after_sync();
         }
@@ -356,26 +327,6 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       // ---- issuer YV: dV += P^T dO (A = P^T from the unit's TMEM slot) of every unit; its commit frees the slot ----
       constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, false, false);   // A = P^T from TMEM, B MN-major (fp16 x fp16)
       const uint64_t ddo_mn = desc_mnmajor<SW>(smem_u32(sDO), 0, Cfg::BOX_BYTES);    // dO_i rows as MN-major B
-      if (Cfg::TILE) {
-        for (int i = 0; i < T; ++i) {
-          const int st = i % NST, pbuf = i % Cfg::NP;
-          if (leader) HSTU_TSTAMP(1, i, 0);
-          mbar_wait(&bars->tile_ready[i & 1], (i >> 1) & 1);  // P^T (TMEM) and dS^T (shared memory) of the tile are written
-          tc_fence_after_sync();
-          const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
-          const uint32_t tp = tmem + Cfg::TMEM_P + pbuf * 64;
-          if (leader) {
-            HSTU_TSTAMP(1, i, 1);
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)  // K = the 128 query rows of the tile; 16 fp16 of P^T per 8 TMEM columns
-              mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (i > 0) || (ks > 0));
-            mma_commit(&bars->p_free[pbuf]);        // the elementwise warpgroups may overwrite this P^T buffer
-            mma_commit(&bars->tile_done[i & 3]);    // this issuer is done with dO_i
-            HSTU_TSTAMP(1, i, 2);
-          }
-          __syncwarp();
-        }
-      } else
       for (int u = 0; u < U; ++u) {
         const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1, slot = u % NSLOT;
         // P^T / dS^T of the unit are written.  One barrier per (half, tile parity): with a 3-slot score ring a warpgroup may
@@ -385,13 +336,14 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         mbar_wait(&bars->unit_done[hf * 2 + pb], (i >> 1) & 1);
         tc_fence_after_sync();
         const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);  // MN-major B: K rows = the 64 query rows
-        const uint32_t tp = tmem + Cfg::TMEM_SLOT + slot * 128;
+        const uint32_t tp = Cfg::PRING ? tmem + Cfg::TMEM_P + (u % Cfg::NPR) * 32 : tmem + Cfg::TMEM_SLOT + slot * 128;
         if (leader) {
           HSTU_TSTAMP(1, u, 1);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
             mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (u > 0) || (ks > 0));
-          mma_commit(&bars->slot_free[slot]);                // the score issuer may overwrite the slot
+          // PRING: the P^T buffer may be rewritten; otherwise: the score issuer may overwrite the slot
+          mma_commit(Cfg::PRING ? &bars->p_free[u % Cfg::NPR] : &bars->slot_free[slot]);
           if (hf == 1) mma_commit(&bars->tile_done[i & 3]);  // this issuer is done with dO_i
           HSTU_TSTAMP(1, u, 2);
         }
@@ -404,26 +356,6 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       constexpr uint32_t idesc_kv = make_idesc(128, D, false, true, false, false);   // A = dS^T K-major, B MN-major (fp16 x fp16)
       const uint64_t dds_k = desc_kmajor<128>(smem_u32(sDST), 0);                    // dS^T box [kv][q] as K-major A
       const uint64_t dq_mn = desc_mnmajor<SW>(smem_u32(sQ), 0, Cfg::BOX_BYTES);      // Q_i rows as MN-major B
-      if (Cfg::TILE) {
-        for (int i = 0; i < T; ++i) {
-          const int st = i % NST, pb = i & 1;
-          if (leader) HSTU_TSTAMP(4, i, 0);
-          mbar_wait(&bars->tile_ready[pb], (i >> 1) & 1);
-          tc_fence_after_sync();
-          const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
-          if (leader) {
-            HSTU_TSTAMP(4, i, 1);
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {  // K = 128 query rows: box ks / 4 of the pair, 32 bytes per step inside the box
-              const uint64_t box = (uint64_t)((pb * Cfg::PT_BYTES + (ks >> 2) * 16384 + (ks & 3) * 32) >> 4);
-              mma_ss(tmem + Cfg::TMEM_DK, dds_k + box, dq_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (i > 0) || (ks > 0));
-            }
-            mma_commit(&bars->tile_done[i & 3]);
-            HSTU_TSTAMP(4, i, 2);
-          }
-          __syncwarp();
-        }
-      } else
       for (int u = 0; u < U; ++u) {
         const int i = u >> 1, hf = u & 1, st = i % NST, pb = i & 1;
         if (leader) HSTU_TSTAMP(4, u, 0);
@@ -452,12 +384,8 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       mbar_wait(kv_rdy, 0);
       for (int i = 0; i < T; ++i) {
         const int pb = i & 1;
-        if (Cfg::TILE) {
-          mbar_wait(&bars->tile_ready[pb], (i >> 1) & 1);
-        } else {
-          mbar_wait(&bars->unit_done[0 * 2 + pb], (i >> 1) & 1);
-          mbar_wait(&bars->unit_done[1 * 2 + pb], (i >> 1) & 1);
-        }
+        mbar_wait(&bars->unit_done[0 * 2 + pb], (i >> 1) & 1);
+        mbar_wait(&bars->unit_done[1 * 2 + pb], (i >> 1) & 1);
         if (i >= Cfg::NDQ) mbar_wait(&bars->dq_empty[i % Cfg::NDQ], ((i / Cfg::NDQ) - 1) & 1);  // dQ_{i-NDQ} has been drained from this accumulator
         tc_fence_after_sync();
         if (leader) {
@@ -635,8 +563,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       const int u = 2 * i + wg, slot = u % Cfg::NSLOT;
       const int m0 = q_tile(i) * 128;
       if (stamp) HSTU_TSTAMP(2 + wg, i, 0);
-      if (Cfg::TILE) mbar_wait(&bars->s_full[0], i & 1);
-      else mbar_wait(&bars->s_full[u % Cfg::NSF], (u / Cfg::NSF) & 1);
+      mbar_wait(&bars->s_full[u % Cfg::NSF], (u / Cfg::NSF) & 1);
       tc_fence_after_sync();
       if (stamp) HSTU_TSTAMP(2 + wg, i, 1);
       // classification of this half-tile (uniform over the warpgroup)
@@ -646,13 +573,11 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + wg * 16384);
       const int jr = j_pos - m0 - cbase;           // query column (relative to this warpgroup's half) equal to j
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
-      // TILE mode: the score slot holds the whole tile (this half starts at column cbase of S^T and of dP^T); unit mode: the
-      // slot holds one half-tile {S^T | dP^T}
-      const uint32_t st_addr = tmem + (Cfg::TILE ? Cfg::TMEM_S + cbase : Cfg::TMEM_SLOT + slot * 128) + lane_bits;
-      const uint32_t dp_addr = tmem + (Cfg::TILE ? Cfg::TMEM_DP + cbase : Cfg::TMEM_SLOT + slot * 128 + 64) + lane_bits;
-      if (Cfg::TILE) {
-        // all 64 scores and 64 dP values of this thread at once, then the slot is released: the score GEMMs of the next tile
-        // run while this warpgroup does its arithmetic
+      const uint32_t st_addr = tmem + Cfg::TMEM_SLOT + slot * 128 + lane_bits;   // the slot holds one half-tile {S^T | dP^T}
+      const uint32_t dp_addr = st_addr + 64;
+      if (Cfg::PRING) {
+        // all 64 scores and 64 dP values of this thread at once, then the slot is handed back: the score GEMMs of this
+        // warpgroup's next unit run while it does its arithmetic
         uint32_t s[2][32], dp[2][32];
         tmem_ld32(st_addr, s[0]);
         tmem_ld32(st_addr + 32, s[1]);
@@ -660,7 +585,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         tmem_ld32(dp_addr + 32, dp[1]);
         tmem_ld_wait();
         tc_fence_before_sync();
-        mbar_arrive(&bars->scores_free);
+        mbar_arrive(&bars->scores_free[wg]);
         uint32_t pp[32], dd[32];
 #define HSTU_S64(e) s[(e) >> 5][(e) & 31]
 #define HSTU_D64(e) dp[(e) >> 5][(e) & 31]
@@ -668,12 +593,12 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
 #undef HSTU_S64
 #undef HSTU_D64
         if (i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
-        if (i >= Cfg::NP) {
-          mbar_wait(&bars->p_free[i % Cfg::NP], ((i / Cfg::NP) - 1) & 1);           // dV of tile i - NP has consumed the P^T buffer
+        if (u >= Cfg::NPR) {
+          mbar_wait(&bars->p_free[u % Cfg::NPR], ((u / Cfg::NPR) - 1) & 1);         // dV of unit u - NPR has consumed the P^T buffer
           tc_fence_after_sync();
         }
-        // P^T: 64 fp16 = 32 columns of the tile's P^T buffer (A of the dV GEMM)
-        const uint32_t p_addr = tmem + Cfg::TMEM_P + (i % Cfg::NP) * 64 + wg * 32 + lane_bits;
+        // P^T: 64 fp16 = the 32 columns of the unit's P^T buffer (A of the dV GEMM)
+        const uint32_t p_addr = tmem + Cfg::TMEM_P + (u % Cfg::NPR) * 32 + lane_bits;
         {
           uint32_t lo[16], hi[16];
 #pragma unroll
@@ -713,8 +638,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       tc_fence_before_sync();
       fence_proxy_async_smem();
       if (stamp) HSTU_TSTAMP(2 + wg, i, 2);
-      if (Cfg::TILE) mbar_arrive(&bars->tile_ready[i & 1]);
-      else mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);
+      mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);
     }
 #undef HSTU_BWD_RUN
 #undef HSTU_BWD_ELEM2

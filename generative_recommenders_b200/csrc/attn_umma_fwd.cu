@@ -270,33 +270,34 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
       const int n0 = (t0 + i) * 128;
       const int mode = (n0 + 128 <= full_lim) ? 0 : (fast ? 1 : 2);  // tile-uniform: no divergence
       const int lim_rel = lim_i - n0, diag_rel = i_pos - n0;
-      // 2 chunks of 64 key columns; the second is loaded while the first is processed.  One straight-line block of 32
-      // independent MUFU -> FFMA2 -> pack chains per chunk (the tile-uniform mask mode selects the block): with 32-column chunks
-      // every block boundary (tcgen05.wait::ld, tcgen05.st) exposed the latency of the chains (r02).
-      uint32_t sbuf[2][2][32];
-      tmem_ld32(s_taddr, sbuf[0][0]);
-      tmem_ld32(s_taddr + 32, sbuf[0][1]);
+      uint32_t sbuf[2][32];
+#ifdef HSTU_EXP_NO_ELEM
+      if (T < 0)  // ablation experiment only: skip the whole elementwise stage
+#endif
+      tmem_ld32(s_taddr, sbuf[0]);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+#ifdef HSTU_EXP_NO_ELEM
+      for (int c = 0; c < (T < 0 ? 4 : 0); ++c) {
+#else
+      for (int c = 0; c < 4; ++c) {
+#endif
         tmem_ld_wait();
-        if (c == 0) {
-          tmem_ld32(s_taddr + 64, sbuf[1][0]);
-          tmem_ld32(s_taddr + 96, sbuf[1][1]);
-        }
-        uint32_t pk[32];
-#define HSTU_FWD_S(e) sbuf[c][(e) >> 5][(e) & 31]
+        if (c < 3) tmem_ld32(s_taddr + (c + 1) * 32, sbuf[(c + 1) & 1]);  // prefetch the next 32 columns
+        const uint32_t(&s)[32] = sbuf[c & 1];
+        uint32_t pk[16];
         if (mode == 0) {
 #pragma unroll
-          for (int e = 0; e < 64; e += 2) {
-            const float2 hh = __fmul2_rn(make_float2(__uint_as_float(HSTU_FWD_S(e)), __uint_as_float(HSTU_FWD_S(e + 1))), ah2);
+          for (int e = 0; e < 32; e += 2) {
+            const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), ah2);
             const float2 pv = __ffma2_rn(hh, make_float2(tanh_approx(hh.x), tanh_approx(hh.y)), hh);
-            pk[e >> 1] = pack_f16x2_sat(pv.x, pv.y);
+            const float p0 = pv.x, p1 = pv.y;
+            pk[e >> 1] = pack_f16x2_sat(p0, p1);
           }
         } else if (mode == 1) {
 #pragma unroll
-          for (int e = 0; e < 64; e += 2) {
-            const int j0 = c * 64 + e;
-            const float2 hh = __fmul2_rn(make_float2(__uint_as_float(HSTU_FWD_S(e)), __uint_as_float(HSTU_FWD_S(e + 1))), ah2);
+          for (int e = 0; e < 32; e += 2) {
+            const int j0 = c * 32 + e;
+            const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), ah2);
             const float2 pv = __ffma2_rn(hh, make_float2(tanh_approx(hh.x), tanh_approx(hh.y)), hh);
             float p0 = pv.x, p1 = pv.y;
             p0 = ((j0 < lim_rel) | (j0 == diag_rel)) ? p0 : 0.f;
@@ -305,9 +306,9 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 64; e += 2) {
-            const int j = n0 + c * 64 + e;
-            const float2 hh = __fmul2_rn(make_float2(__uint_as_float(HSTU_FWD_S(e)), __uint_as_float(HSTU_FWD_S(e + 1))), ah2);
+          for (int e = 0; e < 32; e += 2) {
+            const int j = n0 + c * 32 + e;
+            const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), ah2);
             const float2 pv = __ffma2_rn(hh, make_float2(tanh_approx(hh.x), tanh_approx(hh.y)), hh);
             float p0 = pv.x, p1 = pv.y;
             p0 = (j < len && mask_valid(msk, i_pos, j)) ? p0 : 0.f;
@@ -315,19 +316,9 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
             pk[e >> 1] = pack_f16x2_sat(p0, p1);
           }
         }
-#undef HSTU_FWD_S
-        // P chunk c (64 fp16 = 32 columns) goes to columns [32 c, 32 c + 32) of the slot: a region of S that has already been
-        // read (S chunk c covers columns [64 c, 64 c + 64))
-        {
-          uint32_t lo[16], hi[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            lo[e] = pk[e];
-            hi[e] = pk[16 + e];
-          }
-          tmem_st16(s_taddr + c * 32, lo);
-          tmem_st16(s_taddr + c * 32 + 16, hi);
-        }
+        // P chunk c (32 bf16 = 16 columns) goes to columns [16 c, 16 c + 16) of the slot: a region of S that has already
+        // been read (S chunk c covers columns [32 c, 32 c + 32))
+        tmem_st16(s_taddr + c * 16, pk);
       }
       tmem_st_wait();
       tc_fence_before_sync();

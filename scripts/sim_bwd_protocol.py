@@ -34,55 +34,70 @@ def cfg_for(d):
     return dict(NST={32: 4, 64: 3, 128: 1}[d], NSLOT={32: 3, 64: 2, 128: 1}[d], NDQ={32: 2, 64: 2, 128: 1}[d])
 
 
-def run_tile(T, d, seed):
-    """TILE mode of the kernel (d <= 64): one score slot per query tile, P^T ring of NP buffers, NDQ dQ accumulators."""
+def run_pring(T, d, seed):
+    """PRING mode of the kernel (d <= 64): one score slot per warpgroup, handed back right after the load; P^T ring of NPR
+    buffers released by the dV commits; NDQ dQ accumulators."""
     NST = {32: 4, 64: 3}[d]
-    NP = NDQ = {32: 2, 64: 1}[d]
+    NPR = {32: 4, 64: 2}[d]
+    NDQ = {32: 2, 64: 1}[d]
     rnd = random.Random(seed)
-    B = {"kv": Bar(1), "kvr": Bar(1), "fin": Bar(2), "sf": Bar(1), "free": Bar(2)}
+    B = {"kv": Bar(1), "kvr": Bar(1), "fin": Bar(2)}
     for i in range(4):
-        B[f"qf{i}"], B[f"qr{i}"], B[f"td{i}"] = Bar(1), Bar(1), Bar(3)
+        B[f"qf{i}"], B[f"qr{i}"], B[f"td{i}"], B[f"ud{i}"], B[f"pf{i}"] = Bar(1), Bar(1), Bar(3), Bar(1), Bar(1)
     for i in range(2):
-        B[f"tr{i}"], B[f"pf{i}"], B[f"dqe{i}"] = Bar(2), Bar(1), Bar(1)
+        B[f"sf{i}"], B[f"free{i}"], B[f"dqe{i}"] = Bar(1), Bar(1), Bar(1)
+    U = 2 * T
+
+    def ud(u):
+        i, hf = u >> 1, u & 1
+        return f"ud{hf * 2 + (i & 1)}", i >> 1
 
     def X():
         yield ("wait", "kvr", 0)
-        for i in range(T):
+        for u in range(U):
+            i, hf = u >> 1, u & 1
             if i >= 1:
-                yield ("wait", "free", i - 1)
-            yield ("wait", f"qr{i % NST}", i // NST)
-            yield ("async", "sf")
+                yield ("wait", f"free{hf}", i - 1)
+            if hf == 0:
+                yield ("wait", f"qr{i % NST}", i // NST)
+            yield ("async", f"sf{hf}")
 
     def YV():
-        for i in range(T):
-            yield ("wait", f"tr{i & 1}", i >> 1)
-            yield ("async", f"pf{i % NP}")
-            yield ("async", f"td{i & 3}")
+        for u in range(U):
+            i, hf = u >> 1, u & 1
+            yield ("wait",) + ud(u)
+            yield ("async", f"pf{u % NPR}")
+            if hf == 1:
+                yield ("async", f"td{i & 3}")
         yield ("async", "fin")
 
     def YK():
-        for i in range(T):
-            yield ("wait", f"tr{i & 1}", i >> 1)
-            yield ("async", f"td{i & 3}")
+        for u in range(U):
+            i, hf = u >> 1, u & 1
+            yield ("wait",) + ud(u)
+            if hf == 1:
+                yield ("async", f"td{i & 3}")
         yield ("async", "fin")
 
     def Z():
         yield ("wait", "kvr", 0)
         for i in range(T):
-            yield ("wait", f"tr{i & 1}", i >> 1)
+            yield ("wait",) + ud(2 * i)
+            yield ("wait",) + ud(2 * i + 1)
             if i >= NDQ:
                 yield ("wait", f"dqe{i % NDQ}", i // NDQ - 1)
             yield ("async", f"td{i & 3}")
 
-    def W():
+    def W(h):
         for i in range(T):
-            yield ("wait", "sf", i)
-            yield ("arrive", "free")        # all scores loaded: the score slot may be overwritten
+            u = 2 * i + h
+            yield ("wait", f"sf{h}", i)
+            yield ("arrive", f"free{h}")     # all scores loaded: the slot goes back to the issuer
             if i >= 2:
                 yield ("wait", f"td{(i - 2) & 3}", (i - 2) >> 2)
-            if i >= NP:
-                yield ("wait", f"pf{i % NP}", i // NP - 1)
-            yield ("arrive", f"tr{i & 1}")
+            if u >= NPR:
+                yield ("wait", f"pf{u % NPR}", u // NPR - 1)
+            yield ("arrive", ud(u)[0])
         yield ("wait", "fin", 0)
 
     def Dr():
@@ -103,7 +118,7 @@ def run_tile(T, d, seed):
                 yield ("wait", f"qf{(i + NST) % NST}", (i + NST) // NST)
                 yield ("arrive", f"qr{(i + NST) % NST}")
 
-    actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W0": W(), "W1": W(), "D": Dr()}
+    actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W0": W(0), "W1": W(1), "D": Dr()}
     return _simulate(actors, B, rnd)
 
 
@@ -157,7 +172,7 @@ def _simulate(actors, B, rnd):
 
 def run(T, d, seed, break_ud=False, break_sf=False):
     if d in (32, 64) and not (break_ud or break_sf):
-        return run_tile(T, d, seed)
+        return run_pring(T, d, seed)
     c = cfg_for(d)
     NST, NSLOT, NDQ = c["NST"], c["NSLOT"], c["NDQ"]
     NSF = NSLOT if break_sf else max(NSLOT, 2)
