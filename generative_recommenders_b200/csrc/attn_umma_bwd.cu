@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     for (int i = 0; i < 2; ++i) mbar_init(&bars->dq_empty[i], 128);
     mbar_init(&bars->fin_full, 2);         // YV (dV) and YK (dK)
     mbar_init(&bars->kv_ready, 128);
-    for (int i = 0; i < 4; ++i) mbar_init(&bars->q_ready[i], 128);
+    // Q_i / dO_i tiles are converted by the drain warpgroup (128 arrivals), or -- with a single stage (d = 128), where the
+    // conversion is on the critical path of every tile -- by the two elementwise warpgroups together (256 arrivals)
+    for (int i = 0; i < 4; ++i) mbar_init(&bars->q_ready[i], NST == 1 ? 256 : 128);
     for (int i = 0; i < 3; ++i) mbar_init(&bars->slot_free[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&bars->scores_free[i], 128);
     for (int i = 0; i < 4; ++i) mbar_init(&bars->p_free[i], 1);
@@ -450,7 +452,8 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       convert_bf16_to_f16_inplace<128>(sV, Cfg::TILE_BYTES, ct, 1.0f);
       fence_proxy_async_smem();
       mbar_arrive(&bars->kv_ready);
-      for (int i = 0; i < NST && i < T; ++i) convert_tile(i);
+      if (NST > 1)
+        for (int i = 0; i < NST && i < T; ++i) convert_tile(i);
     }
     int box = 0;  // staging box counter (box & 1 = buffer)
     for (int i = 0; i < T; ++i) {
@@ -482,7 +485,10 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
           bulk_commit_group();
         }
       }
-      if (CONV && i + NST < T) convert_tile(i + NST);  // the load issued above: by now most of its latency has passed
+      // Convert the tile whose load was issued ONE iteration ago (it has landed by now).  Waiting here for the load issued
+      // above would put a full TMA round trip into every iteration of this loop -- and this loop paces the dQ accumulators and
+      // the Q / dO stages of the whole CTA (r02: 2.25 -> 2.9 ms with that wait).
+      if (CONV && NST > 1 && i >= 1 && i - 1 + NST < T) convert_tile(i - 1 + NST);
     }
     if (elected) bulk_wait_group_read0();          // shared memory must stay valid until the last reduce has read it
   } else {
@@ -563,6 +569,15 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       const int u = 2 * i + wg, slot = u % Cfg::NSLOT;
       const int m0 = q_tile(i) * 128;
       if (stamp) HSTU_TSTAMP(2 + wg, i, 0);
+      if (CONV && NST == 1) {
+        // single Q / dO stage: the tile has just landed and nothing else can run before it is converted, so both warpgroups
+        // do it (this one: Q, the other: dO times 2^-e), 256 threads instead of the 128 of the drain warpgroup
+        mbar_wait(&bars->q_full[0], i & 1);
+        if (wg == 0) convert_bf16_to_f16_inplace<128>(sQ, Cfg::TILE_BYTES, tid - 128, 1.0f);
+        else convert_bf16_to_f16_inplace<128>(sDO, Cfg::TILE_BYTES, tid - 256, ds_scale);
+        fence_proxy_async_smem();
+        mbar_arrive(&bars->q_ready[0]);
+      }
       mbar_wait(&bars->s_full[u % Cfg::NSF], (u / Cfg::NSF) & 1);
       tc_fence_after_sync();
       if (stamp) HSTU_TSTAMP(2 + wg, i, 1);

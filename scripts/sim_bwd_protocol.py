@@ -114,9 +114,10 @@ def run_pring(T, d, seed):
             if i + NST < T:
                 yield ("async", f"qf{(i + NST) % NST}")
             yield ("arrive", f"dqe{i % NDQ}")
-            if i + NST < T:
-                yield ("wait", f"qf{(i + NST) % NST}", (i + NST) // NST)
-                yield ("arrive", f"qr{(i + NST) % NST}")
+            t = i - 1 + NST          # the tile whose load was issued one iteration ago
+            if i >= 1 and t < T:
+                yield ("wait", f"qf{t % NST}", t // NST)
+                yield ("arrive", f"qr{t % NST}")
 
     actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W0": W(0), "W1": W(1), "D": Dr()}
     return _simulate(actors, B, rnd)
@@ -181,7 +182,8 @@ def run(T, d, seed, break_ud=False, break_sf=False):
     B = {"kv": Bar(1), "kvr": Bar(1), "fin": Bar(2)}
     for i in range(4):
         B[f"qf{i}"] = Bar(1)
-        B[f"qr{i}"] = Bar(1)       # bf16 inputs: tile converted to fp16 (128 drain threads modelled as one arrival)
+        B[f"qr{i}"] = Bar(2 if NST == 1 else 1)  # bf16 inputs: tile converted to fp16 (by the drain warpgroup, or -- single
+        #                                             stage -- by the two elementwise warpgroups: one arrival each)
         B[f"td{i}"] = Bar(3)       # YV, YK, Z
         B[f"ud{i}"] = Bar(1)       # count 128 threads modelled as one arrival per warpgroup
     for i in range(3):
@@ -236,6 +238,9 @@ def run(T, d, seed, break_ud=False, break_sf=False):
     def W(h):
         for i in range(T):
             u = 2 * i + h
+            if NST == 1:             # single stage: the elementwise warpgroups convert the tile that has just landed
+                yield ("wait", "qf0", i)
+                yield ("arrive", "qr0")
             yield ("wait", f"sf{u % NSF}", u // NSF)
             if i >= 2:
                 yield ("wait", f"td{(i - 2) & 3}", (i - 2) >> 2)
@@ -248,17 +253,19 @@ def run(T, d, seed, break_ud=False, break_sf=False):
             yield ("async", f"qf{i % NST}")
         yield ("wait", "kv", 0)
         yield ("arrive", "kvr")
-        for i in range(min(NST, T)):
-            yield ("wait", f"qf{i % NST}", i // NST)
-            yield ("arrive", f"qr{i % NST}")
+        if NST > 1:
+            for i in range(min(NST, T)):
+                yield ("wait", f"qf{i % NST}", i // NST)
+                yield ("arrive", f"qr{i % NST}")
         for i in range(T):
             yield ("wait", f"td{i & 3}", i >> 2)
             if i + NST < T:
                 yield ("async", f"qf{(i + NST) % NST}")
             yield ("arrive", f"dqe{i % NDQ}")
-            if i + NST < T:
-                yield ("wait", f"qf{(i + NST) % NST}", (i + NST) // NST)
-                yield ("arrive", f"qr{(i + NST) % NST}")
+            t = i - 1 + NST
+            if NST > 1 and i >= 1 and t < T:
+                yield ("wait", f"qf{t % NST}", t // NST)
+                yield ("arrive", f"qr{t % NST}")
 
     actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W0": W(0), "W1": W(1), "D": Dr()}
     pending = {k: None for k in actors}     # the blocking wait of each actor
