@@ -386,11 +386,14 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       mbar_wait(kv_rdy, 0);
       for (int i = 0; i < T; ++i) {
         const int pb = i & 1;
+        if (leader) HSTU_TSTAMP(5, i, 0);
         mbar_wait(&bars->unit_done[0 * 2 + pb], (i >> 1) & 1);
         mbar_wait(&bars->unit_done[1 * 2 + pb], (i >> 1) & 1);
+        if (leader) HSTU_TSTAMP(5, i, 1);
         if (i >= Cfg::NDQ) mbar_wait(&bars->dq_empty[i % Cfg::NDQ], ((i / Cfg::NDQ) - 1) & 1);  // dQ_{i-NDQ} has been drained from this accumulator
         tc_fence_after_sync();
         if (leader) {
+          HSTU_TSTAMP(5, i, 2);
           const uint64_t pair = (uint64_t)((pb * Cfg::PT_BYTES) >> 4);  // the dS^T boxes of this query tile
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)  // K = 128 key rows, 16 per step
@@ -457,8 +460,10 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     }
     int box = 0;  // staging box counter (box & 1 = buffer)
     for (int i = 0; i < T; ++i) {
+      if (elected) HSTU_TSTAMP(6, i, 0);
       mbar_wait(&bars->tile_done[i & 3], (i >> 2) & 1);
       tc_fence_after_sync();
+      if (elected) HSTU_TSTAMP(6, i, 1);
       if (elected && i + NST < T) load_tile(i + NST);
       const int qpos = q_tile(i) * 128 + row;
       const bool q_ok = qpos < len;                // rows past the end of this sequence belong to the next one: add zeros
@@ -488,7 +493,9 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       // Convert the tile whose load was issued ONE iteration ago (it has landed by now).  Waiting here for the load issued
       // above would put a full TMA round trip into every iteration of this loop -- and this loop paces the dQ accumulators and
       // the Q / dO stages of the whole CTA (r02: 2.25 -> 2.9 ms with that wait).
+      if (elected) HSTU_TSTAMP(6, i, 2);
       if (CONV && NST > 1 && i >= 1 && i - 1 + NST < T) convert_tile(i - 1 + NST);
+      if (elected) HSTU_TSTAMP(6, i, 3);
     }
     if (elected) bulk_wait_group_read0();          // shared memory must stay valid until the last reduce has read it
   } else {
@@ -795,7 +802,7 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   dim3 grid((p.max_seq_len + 127) / 128, p.heads, p.batch);
 #ifdef HSTU_TRACE
   long long* tbuf = nullptr;
-  const size_t tbytes = sizeof(long long) * 5 * 256 * 4;
+  const size_t tbytes = sizeof(long long) * 7 * 256 * 4;
   cudaMalloc(&tbuf, tbytes);
   cudaMemset(tbuf, 0, tbytes);
   cudaMemcpyToSymbol(g_trace, &tbuf, sizeof(tbuf));
@@ -805,11 +812,11 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
 #ifdef HSTU_TRACE
   {
     cudaDeviceSynchronize();
-    static long long host[5 * 256 * 4];
+    static long long host[7 * 256 * 4];
     cudaMemcpy(host, tbuf, tbytes, cudaMemcpyDeviceToHost);
     FILE* f = fopen("gpurun_out/bwd_trace.txt", "w");
     if (f) {
-      for (int r = 0; r < 5; ++r)
+      for (int r = 0; r < 7; ++r)
         for (int i = 0; i < 256; ++i) {
           const long long* e = host + (r * 256 + i) * 4;
           if (e[0] || e[1] || e[2] || e[3]) fprintf(f, "%d %d %lld %lld %lld %lld\n", r, i, e[0], e[1], e[2], e[3]);
