@@ -125,6 +125,10 @@ struct BwdBars {
   uint32_t tmem_base;
 };
 
+#ifndef HSTU_BWD_STAGGER_CLK
+#define HSTU_BWD_STAGGER_CLK 1300
+#endif
+
 #ifdef HSTU_TRACE
 // Debug timeline: CTA (0,0,0) records clock64() stamps of its pipeline events into g_trace[role][index][slot].
 __device__ long long* g_trace = nullptr;
@@ -572,6 +576,14 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     }                                                                                                          \
   }
 
+    if (Cfg::PRING && wg == 1 && T >= 2) {
+      // The two warpgroups share the MUFU / pack pipe and each has a load / store / barrier phase of ~700 clk per unit in which
+      // it needs none of it.  Started together they stay in lockstep (nothing couples or decouples them once the scores are
+      // always early) and those phases coincide; half a unit of initial offset lets one group's arithmetic cover the other's gap.
+      const long long t_start = clock64();
+      while (clock64() - t_start < HSTU_BWD_STAGGER_CLK) {
+      }
+    }
     for (int i = 0; i < T; ++i) {
       const int u = 2 * i + wg, slot = u % Cfg::NSLOT;
       const int m0 = q_tile(i) * 128;
