@@ -125,10 +125,6 @@ struct BwdBars {
   uint32_t tmem_base;
 };
 
-#ifndef HSTU_BWD_STAGGER_CLK
-#define HSTU_BWD_STAGGER_CLK 1300
-#endif
-
 #ifdef HSTU_TRACE
 // Debug timeline: CTA (0,0,0) records clock64() stamps of its pipeline events into g_trace[role][index][slot].
 __device__ long long* g_trace = nullptr;
@@ -576,14 +572,6 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     }                                                                                                          \
   }
 
-    if (Cfg::PRING && wg == 1 && T >= 2) {
-      // The two warpgroups share the MUFU / pack pipe and each has a load / store / barrier phase of ~700 clk per unit in which
-      // it needs none of it.  Started together they stay in lockstep (nothing couples or decouples them once the scores are
-      // always early) and those phases coincide; half a unit of initial offset lets one group's arithmetic cover the other's gap.
-      const long long t_start = clock64();
-      while (clock64() - t_start < HSTU_BWD_STAGGER_CLK) {
-      }
-    }
     for (int i = 0; i < T; ++i) {
       const int u = 2 * i + wg, slot = u % Cfg::NSLOT;
       const int m0 = q_tile(i) * 128;
@@ -610,43 +598,41 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       const uint32_t st_addr = tmem + Cfg::TMEM_SLOT + slot * 128 + lane_bits;   // the slot holds one half-tile {S^T | dP^T}
       const uint32_t dp_addr = st_addr + 64;
       if (Cfg::PRING) {
-        // all 64 scores and 64 dP values of this thread at once, then the slot is handed back: the score GEMMs of this
-        // warpgroup's next unit run while it does its arithmetic
+        // Two chunks of 32 query columns; the second is loaded while the first is processed, and as soon as it has landed the
+        // slot goes back to the issuer (scores_free): the score GEMMs of this warpgroup's next unit run during the second half
+        // of its arithmetic.  (Loading all 64 + 64 values first and processing them as one block left ptxas no registers to
+        // interleave the last MUFU -> FFMA2 chains: 2500 clk per unit instead of 1700, profiles/r02_bwd_timelines.txt (E).)
         uint32_t s[2][32], dp[2][32];
         tmem_ld32(st_addr, s[0]);
-        tmem_ld32(st_addr + 32, s[1]);
         tmem_ld32(dp_addr, dp[0]);
-        tmem_ld32(dp_addr + 32, dp[1]);
         tmem_ld_wait();
-        tc_fence_before_sync();
-        mbar_arrive(&bars->scores_free[wg]);
-        uint32_t pp[32], dd[32];
-#define HSTU_S64(e) s[(e) >> 5][(e) & 31]
-#define HSTU_D64(e) dp[(e) >> 5][(e) & 31]
-        HSTU_BWD_RUN(64, HSTU_S64, HSTU_D64, pp, dd, 0);
-#undef HSTU_S64
-#undef HSTU_D64
-        if (i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
-        if (u >= Cfg::NPR) {
-          mbar_wait(&bars->p_free[u % Cfg::NPR], ((u / Cfg::NPR) - 1) & 1);         // dV of unit u - NPR has consumed the P^T buffer
-          tc_fence_after_sync();
-        }
-        // P^T: 64 fp16 = the 32 columns of the unit's P^T buffer (A of the dV GEMM)
-        const uint32_t p_addr = tmem + Cfg::TMEM_P + (u % Cfg::NPR) * 32 + lane_bits;
-        {
-          uint32_t lo[16], hi[16];
+        tmem_ld32(st_addr + 32, s[1]);
+        tmem_ld32(dp_addr + 32, dp[1]);
+        const uint32_t p_addr = tmem + Cfg::TMEM_P + (u % Cfg::NPR) * 32 + lane_bits;  // 64 fp16 = 32 columns: A of the dV GEMM
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            lo[e] = pp[e];
-            hi[e] = pp[16 + e];
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pp[16], dd[16];
+#define HSTU_SC(e) s[c][e]
+#define HSTU_DC(e) dp[c][e]
+          HSTU_BWD_RUN(32, HSTU_SC, HSTU_DC, pp, dd, c * 32);
+#undef HSTU_SC
+#undef HSTU_DC
+          if (c == 0) {
+            tmem_ld_wait();               // chunk 1 is in registers: the slot is free
+            tc_fence_before_sync();
+            mbar_arrive(&bars->scores_free[wg]);
+            if (i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
+            if (u >= Cfg::NPR) {
+              mbar_wait(&bars->p_free[u % Cfg::NPR], ((u / Cfg::NPR) - 1) & 1);         // dV of unit u - NPR has consumed the P^T buffer
+              tc_fence_after_sync();
+            }
           }
-          tmem_st16(p_addr, lo);
-          tmem_st16(p_addr + 16, hi);
-        }
-        // dS^T [kv][q] (16-byte stores): A of dK as stored, A of dQ read MN-major
+          tmem_st16(p_addr + c * 16, pp);
+          // dS^T [kv][q] (16-byte stores): A of dK as stored, A of dQ read MN-major
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c), dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
+          for (int j4 = 0; j4 < 4; ++j4)
+            st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + j4), dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
+        }
       } else {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {  // 2 chunks of 32 query columns
