@@ -275,6 +275,9 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
 // significand exactly; magnitudes above 65504 saturate and magnitudes below 2^-24 flush to zero.
 template <int NT>
 __device__ __forceinline__ void convert_bf16_to_f16_inplace(uint8_t* base, int bytes, int t, float scale) {
+#ifdef HSTU_EXP_NO_CONVERT
+  if (bytes > 0) return;  // ablation experiment only (wrong numerics): what does the in-place conversion cost?
+#endif
   const uint32_t s0 = smem_u32(base);
   constexpr int U = 4;  // independent 16-byte chunks in flight per thread (the loop is latency-bound otherwise)
   for (int off0 = t * 16; off0 < bytes; off0 += U * NT * 16) {
