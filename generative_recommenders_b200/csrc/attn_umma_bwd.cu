@@ -91,10 +91,13 @@ struct BwdCfg {
   // pipe busy through each other's load / store phases.  (A whole-tile variant with one 256-column slot and N = 128 score MMAs,
   // (C) / (D) in the same file, has 28 % less tensor-pipe work but forces both warpgroups into lockstep: 2.8 ms instead of 2.25.)
   // d = 128 keeps the r01 layout: its dK / dV accumulators leave room for one slot only and none for a P^T ring.
-  static constexpr bool PRING = D <= 64;
-  static constexpr int NSLOT = PRING ? 2 : 1;
+#ifndef HSTU_BWD_PRING
+#define HSTU_BWD_PRING 1
+#endif
+  static constexpr bool PRING = HSTU_BWD_PRING && D <= 64;
+  static constexpr int NSLOT = PRING ? 2 : (D <= 32 ? 3 : (D == 64 ? 2 : 1));
   static constexpr int NPR = (D <= 32) ? 4 : 2;  // PRING: P^T buffers (unit u -> u % NPR)
-  static constexpr int NDQ = (D <= 32) ? 2 : 1;
+  static constexpr int NDQ = (D <= 32) ? 2 : ((D == 64 && !PRING) ? 2 : 1);
   // s_full barrier instances: unit u -> [u % NSF].  At least two even with one slot: the warpgroups alternate units, and a
   // warpgroup must never wait for phase k+1 of a barrier before phase k has completed (the parity test would pass at once).
   static constexpr int NSF = NSLOT < 2 ? 2 : NSLOT;
