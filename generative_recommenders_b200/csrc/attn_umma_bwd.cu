@@ -92,7 +92,7 @@ struct BwdCfg {
   // (C) / (D) in the same file, has 28 % less tensor-pipe work but forces both warpgroups into lockstep: 2.8 ms instead of 2.25.)
   // d = 128 keeps the r01 layout: its dK / dV accumulators leave room for one slot only and none for a P^T ring.
 #ifndef HSTU_BWD_PRING
-#define HSTU_BWD_PRING 1
+#define HSTU_BWD_PRING 0
 #endif
   static constexpr bool PRING = HSTU_BWD_PRING && D <= 64;
   static constexpr int NSLOT = PRING ? 2 : (D <= 32 ? 3 : (D == 64 ? 2 : 1));
@@ -497,7 +497,11 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       // above would put a full TMA round trip into every iteration of this loop -- and this loop paces the dQ accumulators and
       // the Q / dO stages of the whole CTA (r02: 2.25 -> 2.9 ms with that wait).
       if (elected) HSTU_TSTAMP(6, i, 2);
-      if (CONV && NST > 1 && i >= 1 && i - 1 + NST < T) convert_tile(i - 1 + NST);
+      if (CONV && NST >= 4) {
+        if (i >= 1 && i - 1 + NST < T) convert_tile(i - 1 + NST);
+      } else if (CONV && NST > 1 && i + NST < T) {
+        convert_tile(i + NST);  // three stages (d = 64): the lag would leave the issuer one tile short; take the wait instead
+      }
       if (elected) HSTU_TSTAMP(6, i, 3);
     }
     if (elected) bulk_wait_group_read0();          // shared memory must stay valid until the last reduce has read it
@@ -513,25 +517,28 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     // dS^T is an fp16 tensor-core operand: it is stored as dS * 2^-e.  With bf16 inputs the factor is already in dO (applied
     // when dO was converted); with fp16 inputs it is folded into the constants of the sigmoid-derivative polynomial here.
     // It is removed again in the dK / dV epilogues and in dq_convert_kernel.
-    const float ew_scale = CONV ? 1.0f : ds_scale;
-    const float2 shalf2v = make_float2(0.5f * ew_scale, 0.5f * ew_scale), nshalf2v = make_float2(-0.5f * ew_scale, -0.5f * ew_scale);
+    // The derivative factor g = sig (1 + x (1 - sig)) is evaluated as (1 + g2) / 2 with g2 = t + h (1 - t^2), t = tanh(h), h = x / 2
+    // (3 packed FMAs); the 1/2 is left out here and applied with the other factors in the epilogues: dS^T holds 2 * 2^-e * dS.
+    const float2 one2v = make_float2(1.0f, 1.0f);
+    const float2 esc2v = make_float2(ds_scale, ds_scale);
     const bool fast = msk.fast != 0;
     const bool j_ok = j_pos < len;
     const bool j_hist = j_ok && (!msk.has_tgt || j_pos < msk.max_id);  // fast mask: valid = (j_hist & i > j) | (i == j)
     const int cbase = wg * 64;
     const bool stamp = quad == 0 && lane == 0;
 
-    // p = x sig(x) and g = sig (1 + x (1 - sig)) from one tanh: x = 2 hh, sig = (1 + t) / 2
-    // packed fp32x2 arithmetic (FMUL2 / FFMA2): two elements per issued instruction, one MUFU.TANH per element
+    // p = x sig(x) and 2 dS = dP (1 + g2) from one tanh; packed fp32x2 arithmetic (FMUL2 / FFMA2): two elements per issued
+    // instruction, one MUFU.TANH per element
 #define HSTU_BWD_ELEM2(S0, S1, DP0, DP1, P0, P1, D0, D1)                                                       \
   {                                                                                                            \
     const float2 hh = __fmul2_rn(make_float2(__uint_as_float(S0), __uint_as_float(S1)), ah2);                  \
     const float2 t = make_float2(tanh_approx(hh.x), tanh_approx(hh.y));                                        \
-    const float2 pv = __ffma2_rn(hh, t, hh);                                                                   \
-    const float2 sig = __ffma2_rn(shalf2v, t, shalf2v);   /* scale * sig        */                             \
-    const float2 onem = __ffma2_rn(nshalf2v, t, shalf2v); /* scale * (1 - sig)  */                             \
-    const float2 dv = __fmul2_rn(make_float2(__uint_as_float(DP0), __uint_as_float(DP1)),                      \
-                                 __ffma2_rn(pv, onem, sig));                                                   \
+    const float2 pv = __ffma2_rn(hh, t, hh);                    /* p = x sig(x) = h (1 + t)            */      \
+    const float2 w = __ffma2_rn(make_float2(-t.x, -t.y), t, one2v);  /* 1 - t^2                          */      \
+    const float2 g2 = __ffma2_rn(hh, w, t);                     /* 2 g - 1 = t + h (1 - t^2)           */      \
+    float2 dpe = make_float2(__uint_as_float(DP0), __uint_as_float(DP1));                                      \
+    if (!CONV) dpe = __fmul2_rn(dpe, esc2v);                    /* fp16 inputs: dO is not pre-scaled   */      \
+    const float2 dv = __ffma2_rn(dpe, g2, dpe);                 /* 2 dS = dP (1 + g2)                  */      \
     P0 = pv.x; P1 = pv.y; D0 = dv.x; D1 = dv.y;                                                                \
   }
     // NE consecutive query columns starting at column `col0` of this half: scores / dP (SREF(e), DREF(e) = element e of the run)
@@ -672,7 +679,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     const int ecol0 = 0;
     const uint32_t acc = tmem + (is_dv ? Cfg::TMEM_DV : Cfg::TMEM_DK) + ecol0 + lane_bits;
     // undo 2^-e (a power of two: exact): dK always carries it, dV only when dO itself was scaled
-    const float scale = is_dv ? (CONV ? p.dv_scale / ds_scale : p.dv_scale) : p.dk_scale / ds_scale;
+    const float scale = is_dv ? (CONV ? p.dv_scale / ds_scale : p.dv_scale) : 0.5f * p.dk_scale / ds_scale;  // dS^T holds 2 * 2^-e * dS
     uint16_t* gptr = (is_dv
         ? reinterpret_cast<uint16_t*>(p.dv) + (row0 + j_pos) * p.dv_row_stride + (long long)h * p.dv_head_stride
         : reinterpret_cast<uint16_t*>(p.dk) + (row0 + j_pos) * p.dk_row_stride + (long long)h * p.dk_head_stride) + ecol0;
@@ -704,7 +711,7 @@ template <bool BF16>
 __global__ void dq_convert_kernel(const float* __restrict__ acc, uint16_t* __restrict__ dq, long long rows, int heads, int D,
                                   long long row_stride, long long head_stride, float scale_in,
                                   const uint32_t* __restrict__ amax_bits) {
-  const float scale = scale_in / ds_scale_from_amax(__ldg(amax_bits));  // dq_acc holds alpha-less, 2^-e scaled sums
+  const float scale = 0.5f * scale_in / ds_scale_from_amax(__ldg(amax_bits));  // dq_acc holds sums of 2 * 2^-e * dS K (no alpha)
   const long long nvec = rows * heads * (D / 8);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(idx % (D / 8));

@@ -29,8 +29,7 @@ class Violation(Exception):
 
 
 def cfg_for(d):
-    # unit mode of the kernel (d = 128 in the product; the d = 32 / 64 rows describe the r01 configuration and are only used by
-    # the two bug-reproduction tests)
+    # the product configuration: Q / dO stages, score slots (P^T written over the scores of its unit), dQ accumulators
     return dict(NST={32: 4, 64: 3, 128: 1}[d], NSLOT={32: 3, 64: 2, 128: 1}[d], NDQ={32: 2, 64: 2, 128: 1}[d])
 
 
@@ -172,8 +171,6 @@ def _simulate(actors, B, rnd):
 
 
 def run(T, d, seed, break_ud=False, break_sf=False):
-    if d in (32, 64) and not (break_ud or break_sf):
-        return run_pring(T, d, seed)
     c = cfg_for(d)
     NST, NSLOT, NDQ = c["NST"], c["NSLOT"], c["NDQ"]
     NSF = NSLOT if break_sf else max(NSLOT, 2)
@@ -262,8 +259,9 @@ def run(T, d, seed, break_ud=False, break_sf=False):
             if i + NST < T:
                 yield ("async", f"qf{(i + NST) % NST}")
             yield ("arrive", f"dqe{i % NDQ}")
-            t = i - 1 + NST
-            if NST > 1 and i >= 1 and t < T:
+            # four stages: convert the tile whose load was issued one iteration ago; three: the one just issued (blocking)
+            t = i - 1 + NST if NST >= 4 else i + NST
+            if NST > 1 and (i >= 1 or NST < 4) and t < T:
                 yield ("wait", f"qf{t % NST}", t // NST)
                 yield ("arrive", f"qr{t % NST}")
 
@@ -313,6 +311,11 @@ def run(T, d, seed, break_ud=False, break_sf=False):
             state = {k: pending[k] for k in actors if k not in done}
             raise Violation(f"deadlock: {state}")
     return steps
+
+
+def run_variant_pring(T, d, seed):
+    """The PRING variant (compile with -DHSTU_BWD_PRING=1): measured slower than the default on B200, kept switchable."""
+    return run_pring(T, d, seed)
 
 
 if __name__ == "__main__":

@@ -18,6 +18,13 @@ def test_protocol_has_no_deadlock_or_phase_aliasing(d):
             sim.run(tiles, d, seed)
 
 
+@pytest.mark.parametrize("d", [32, 64])
+def test_pring_variant_protocol(d):
+    for tiles in (1, 2, 3, 5, 8, 21):
+        for seed in range(15):
+            sim.run_variant_pring(tiles, d, seed)
+
+
 def test_model_reproduces_the_two_bugs_found_on_the_gpu():
     # one s_full barrier with a single score slot: warpgroup 1 asks for phase 1 before phase 0 completed
     with pytest.raises(sim.Violation, match="false pass"):
