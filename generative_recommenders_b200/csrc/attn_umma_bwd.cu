@@ -82,7 +82,7 @@ struct BwdCfg {
   // dK accumulators and NDQ dQ accumulators (tile i -> buffer i % NDQ; with two, the warpgroups drain dQ two tiles late and
   // never wait for it).  d = 128 fills TMEM with one slot and one dQ accumulator: 128 + 3 * 128 columns.
   //
-  // PRING mode (d <= 64), r02.  In r01 the slot of a unit also carried its P^T (written over the scores), so the issuer of the
+  // PRING mode, r02.  In r01 the slot of a unit also carried its P^T (written over the scores), so the issuer of the
   // scores had to wait for the dV GEMM of the unit three back: a dependency cycle X -> elementwise -> YV -> X of ~3700 clk per
   // three units that set the pace of the CTA (profiles/r02_bwd_timelines.txt (A)).  Now P^T goes to its own small ring of NPR
   // buffers (32 columns each) and a warpgroup loads ALL its scores (64 + 64 registers) before it starts the arithmetic: each
@@ -91,10 +91,12 @@ struct BwdCfg {
   // pipe busy through each other's load / store phases.  (A whole-tile variant with one 256-column slot and N = 128 score MMAs,
   // (C) / (D) in the same file, has 28 % less tensor-pipe work but forces both warpgroups into lockstep: 2.8 ms instead of 2.25.)
   // d = 128 keeps the r01 layout: its dK / dV accumulators leave room for one slot only and none for a P^T ring.
-#ifndef HSTU_BWD_PRING
-#define HSTU_BWD_PRING 0
+  // Measured on B200 (bwd ms, bf16; profiles/r02_bwd_variants.txt): d = 32 (B 16, H 8, Lmax 8192): ring of 3 slots 2.36, PRING 2.77;
+  // d = 64 (B 512, H 4, Lmax 2048): ring of 2 slots 5.55, PRING 5.04.  So PRING is used where it wins: d = 64.
+#ifndef HSTU_BWD_PRING_MASK
+#define HSTU_BWD_PRING_MASK 64   /* bit mask over head dims: 32 | 64 */
 #endif
-  static constexpr bool PRING = HSTU_BWD_PRING && D <= 64;
+  static constexpr bool PRING = (HSTU_BWD_PRING_MASK & D) != 0 && D <= 64;
   static constexpr int NSLOT = PRING ? 2 : (D <= 32 ? 3 : (D == 64 ? 2 : 1));
   static constexpr int NPR = (D <= 32) ? 4 : 2;  // PRING: P^T buffers (unit u -> u % NPR)
   static constexpr int NDQ = (D <= 32) ? 2 : ((D == 64 && !PRING) ? 2 : 1);
