@@ -461,6 +461,52 @@ def run_triton(args):
 # ----------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference eager path on the host cores
 # ----------------------------------------------------------------------------------------------------------------
+_REF_LAYER = None
+
+
+def reference_layer():
+    """The reference's OWN eager STULayer (unmodified Python, fetched into the git-ignored oracle/_ref/ by
+    scripts/fetch_reference_eager.py; fbgemm_gpu's three jagged ops come from oracle/fbgemm_shim.py), HammerKernel.PYTORCH, fp32.
+    None if oracle/_ref is absent (then the oracle port is timed instead)."""
+    global _REF_LAYER
+    if _REF_LAYER is None:
+        ref_root = os.path.join(ROOT, "oracle", "_ref")
+        if not os.path.isdir(os.path.join(ref_root, "generative_recommenders")):
+            _REF_LAYER = False
+            return None
+        try:
+            sys.path.insert(0, ref_root)
+            from oracle import fbgemm_shim
+
+            fbgemm_shim.install()
+            import warnings
+
+            warnings.filterwarnings("ignore")
+            from generative_recommenders.common import HammerKernel as RefKernel
+            from generative_recommenders.modules.stu import STULayer as RefLayer, STULayerConfig as RefConfig
+
+            torch.manual_seed(7)
+            layer = RefLayer(RefConfig(embedding_dim=256, num_heads=8, hidden_dim=32, attention_dim=32, output_dropout_ratio=0.0,
+                                       causal=True, target_aware=True))
+            layer.recursive_setattr("_hammer_kernel", RefKernel.PYTORCH) if hasattr(layer, "recursive_setattr") else \
+                layer.set_hammer_kernel(RefKernel.PYTORCH)
+            assert layer.hammer_kernel() == RefKernel.PYTORCH
+            _REF_LAYER = layer
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"reference eager layer unavailable ({type(e).__name__}: {e}); timing the oracle port instead\n")
+            _REF_LAYER = False
+    return _REF_LAYER or None
+
+
+def cpu_kind():
+    return "reference" if reference_layer() is not None else "port"
+
+
+def cpu_engine_name():
+    return ("reference eager STULayer (unmodified generative_recommenders code from oracle/_ref + fbgemm shim, HammerKernel.PYTORCH)"
+            if reference_layer() is not None else "oracle (fp32 CPU port of the reference eager path)")
+
+
 def cpu_sample(args, layers_sampled: int, prefix: int = 0):
     """One sequence (the first of the seeded batch) -- or, if `prefix` > 0, its first `prefix` rows (a causal prefix of a user
     history is itself a valid, shorter history) -- through `layers_sampled` independent STU layers fwd+bwd in fp32 on CPU.
@@ -481,9 +527,16 @@ def cpu_sample(args, layers_sampled: int, prefix: int = 0):
               "_uvqk_weight": torch.randn(D, Wd) * 0.05, "_uvqk_beta": torch.zeros(Wd),
               "_output_norm_weight": torch.ones(H * dh), "_output_norm_bias": torch.zeros(H * dh),
               "_output_weight": torch.randn(3 * H * dh, D) * 0.05}
+    ref = reference_layer()
     t0 = time.perf_counter()
     for _ in range(layers_sampled):
-        O.stu_layer_fwd_bwd_timed(x, off, lmax, nt, params, H, dh, dh)
+        if ref is not None:
+            xx = x.detach().clone().requires_grad_()
+            n_pad = length if prefix > 0 else lmax  # the eager path pads to max_seq_len: a prefix is its own (shorter) problem
+            y = ref(x=xx, x_lengths=torch.tensor([length]), x_offsets=off, max_seq_len=n_pad, num_targets=nt)
+            y.backward(torch.ones_like(y))
+        else:
+            O.stu_layer_fwd_bwd_timed(x, off, lmax, nt, params, H, dh, dh)
     return time.perf_counter() - t0, length, full
 
 
@@ -505,15 +558,15 @@ def pick_cpu_threads(args, probe_rows: int):
 
 def cpu_baseline(args, seconds_budget: float):
     if args.workload != "hstu_large":
-        return {"value": None, "unit": "sequences/s", "cores": os.cpu_count() or 1, "kind": "port",
+        return {"value": None, "unit": "sequences/s", "cores": os.cpu_count() or 1, "kind": cpu_kind(),
                 "sample": "not measured for this workload"}
     cores, host_cores = pick_cpu_threads(args, max(256, min(1024, args.lmax // 8)))
     t1, length, _ = cpu_sample(args, 1)  # also the warm-up
     n = max(1, min(args.layers, int(seconds_budget / max(t1, 1e-3))))
     t, _, _ = cpu_sample(args, n)
     per_seq = t / n * args.layers
-    return {"value": 1.0 / per_seq, "unit": "sequences/s", "cores": cores, "kind": "port",
-            "sample": f"oracle (fp32 CPU port of the reference eager path), 1 user sequence of length {length}, {n} of "
+    return {"value": 1.0 / per_seq, "unit": "sequences/s", "cores": cores, "kind": cpu_kind(),
+            "sample": f"{cpu_engine_name()}, fp32, 1 user sequence of length {length}, {n} of "
                       f"{args.layers} STU layers fwd+bwd in {t:.1f} s, scaled x{args.layers / n:.1f} to the full stack; "
                       f"{cores} threads (fastest of the probed settings on this {host_cores}-core host)"}
 
@@ -562,10 +615,9 @@ def run_reference(args):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"HSTU-large stack fwd+bwd: {args.layers} layers, D=256, H=8, dqk=dv=32, Lmax={args.lmax} "
-                               "(CPU port of the reference eager path; each step = a bounded sample, scaled to one sequence "
-                               "through the stack)"},
-        "cpu_baseline": {"value": value, "unit": "sequences/s", "cores": cores, "kind": "port",
-                         "sample": f"{what}, fp32, {cores} threads (fastest of the probed settings on this {host_cores}-core host); "
+                               f"({cpu_engine_name()}; each step = a bounded sample, scaled to one sequence through the stack)"},
+        "cpu_baseline": {"value": value, "unit": "sequences/s", "cores": cores, "kind": cpu_kind(),
+                         "sample": f"{cpu_engine_name()}: {what}, fp32, {cores} threads (fastest of the probed settings on this {host_cores}-core host); "
                                    f"scaled x{args.layers} layers"},
         "e2e": {"value": value, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -82,7 +82,6 @@ _PROTOS = {
     "hstu_jagged_dense_bmm_wgrad": (C.c_int, [_vp] * 5 + [_i32] * 6 + [_vp]),
     "hstu_sampled_softmax_fwd": (C.c_int, [C.POINTER(SslParams), _vp]),
     "hstu_sampled_softmax_bwd": (C.c_int, [C.POINTER(SslParams), _vp]),
-    "hstu_umma_selftest": (C.c_int, [C.c_char_p, C.c_size_t]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS.keys())
@@ -106,6 +105,23 @@ def lib() -> C.CDLL:
             raise RuntimeError("libhstu_b200.so ABI version mismatch")
         _lib = l
     return _lib
+
+
+_selftest: Optional[C.CDLL] = None
+
+
+def selftest_lib() -> C.CDLL:
+    """The TEST library with the tcgen05 / TMA self test (include/hstu_b200_selftest.h); not used by any product code path."""
+    global _selftest
+    if _selftest is None:
+        path = os.path.join(_HERE, "lib", "libhstu_b200_selftest.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: build it with `python -m generative_recommenders_b200.build`")
+        l = C.CDLL(path)
+        l.hstu_umma_selftest.restype = C.c_int
+        l.hstu_umma_selftest.argtypes = [C.c_char_p, C.c_size_t]
+        _selftest = l
+    return _selftest
 
 
 # ---- instrumentation used by bench.py: kernel-launch counter and optional CUDA-event timing per C-ABI call ----

@@ -4,7 +4,7 @@
 
 Each translation unit under csrc/ is compiled with
     nvcc -std=c++20 -gencode arch=compute_100a,code=sm_100a -lineinfo -O3
-and linked into generative_recommenders_b200/lib/libhstu_b200.so (git-ignored; it travels to the GPU box with the
+and linked into generative_recommenders_b200/lib/libhstu_b200.so (+ the test-only libhstu_b200_selftest.so; git-ignored; it travels to the GPU box with the
 repo snapshot).  nvcc cross-compiles without a GPU, so this is also the "does it build" check of __graft_entry__.build().
 """
 import concurrent.futures
@@ -18,8 +18,10 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(ROOT, "build", "hstu_b200")
 LIB = os.path.join(HERE, "lib", "libhstu_b200.so")
+SELFTEST_LIB = os.path.join(HERE, "lib", "libhstu_b200_selftest.so")  # test infrastructure: tcgen05 / TMA self test + micro-benchmarks
 
-SOURCES = ["api.cu", "attn_generic.cu", "attn_umma_fwd.cu", "attn_umma_bwd.cu", "umma_selftest.cu", "tmap.cu", "norm.cu", "jagged.cu", "position.cu", "sampled_softmax.cu", "jagged_bmm.cu"]
+SELFTEST_SOURCES = ["umma_selftest.cu", "tmap.cu"]
+SOURCES = ["api.cu", "attn_generic.cu", "attn_umma_fwd.cu", "attn_umma_bwd.cu", "tmap.cu", "norm.cu", "jagged.cu", "position.cu", "sampled_softmax.cu", "jagged_bmm.cu"]
 NVCC_FLAGS = [
     "-std=c++20", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcudafe", "--diag_suppress=177",
@@ -39,7 +41,7 @@ def _deps_mtime() -> float:
 
 
 def is_fresh() -> bool:
-    return os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime()
+    return all(os.path.exists(p) and os.path.getmtime(p) >= _deps_mtime() for p in (LIB, SELFTEST_LIB))
 
 
 def _compile(src: str, extra) -> str:
@@ -71,12 +73,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         extra.append("-DHSTU_DEBUG_SPIN")
     for flag in os.environ.get("HSTU_EXP", "").split():
         extra.append("-D" + flag)
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, extra), SOURCES))
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    all_src = list(dict.fromkeys(SOURCES + SELFTEST_SOURCES))
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(all_src))) as ex:
+        objs = dict(zip(all_src, ex.map(lambda s: _compile(s, extra), all_src)))
+    for lib, srcs in ((LIB, SOURCES), (SELFTEST_LIB, SELFTEST_SOURCES)):
+        cmd = [_nvcc(), "-shared", "-o", lib] + [objs[s] for s in srcs] + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
 
 

@@ -326,6 +326,5 @@ int hstu_sampled_softmax_bwd(const hstu_ssl_params* p, void* stream) {
   return sampled_softmax_bwd(*p, p->dtype, (cudaStream_t)stream);
 }
 
-int hstu_umma_selftest(char* report, size_t report_bytes) { return umma_selftest(report, report_bytes); }
 
 }  // extern "C"

@@ -45,6 +45,17 @@ struct RowIO {
       }
     }
   }
+  // L2 prefetch of the lane's part of a row (the row a warp will process in its NEXT iteration): a warp works on one row at a
+  // time, so without it only one row of loads per warp is in flight and the kernels are bound by HBM latency, not bandwidth
+  static __device__ __forceinline__ void prefetch(const T* row, int D, int lane) {
+    if constexpr (VEC > 1) {
+#pragma unroll
+      for (int k = 0; k < PL / VEC; ++k) {
+        const int c = (k * 32 + lane) * VEC;
+        if (c < D) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + c));
+      }
+    }
+  }
   static __device__ __forceinline__ void store(T* row, int D, int lane, const float (&v)[PL]) {
 #pragma unroll
     for (int k = 0; k < PL / VEC; ++k) {
@@ -133,8 +144,10 @@ __global__ void __launch_bounds__(kNormThreads) ln_fwd_kernel(const T* __restric
   if (w) RowIO<T, VEC, PL>::load(w, D, lane, wv);
   if (b) RowIO<T, VEC, PL>::load(b, D, lane, bv);
   const float inv_d = 1.0f / (float)D;
-  for (long long r = (long long)blockIdx.x * kNormWarps + warp; r < n_rows; r += (long long)gridDim.x * kNormWarps) {
+  const long long rstep = (long long)gridDim.x * kNormWarps;
+  for (long long r = (long long)blockIdx.x * kNormWarps + warp; r < n_rows; r += rstep) {
     float v[PL];
+    if (r + rstep < n_rows) RowIO<T, VEC, PL>::prefetch(x + (r + rstep) * xs, D, lane);
     RowIO<T, VEC, PL>::load(x + r * xs, D, lane, v);
     float mean = 0.f;
     if constexpr (!RMS) {
@@ -184,8 +197,13 @@ __global__ void __launch_bounds__(kNormThreads) ln_bwd_kernel(const T* __restric
 #pragma unroll
   for (int i = 0; i < PL; ++i) aw[i] = ab[i] = 0.f;
   const float inv_d = 1.0f / (float)D;
-  for (long long r = (long long)blockIdx.x * kNormWarps + warp; r < n_rows; r += (long long)gridDim.x * kNormWarps) {
+  const long long rstep = (long long)gridDim.x * kNormWarps;
+  for (long long r = (long long)blockIdx.x * kNormWarps + warp; r < n_rows; r += rstep) {
     float xv[PL], g[PL];
+    if (r + rstep < n_rows) {
+      RowIO<T, VEC, PL>::prefetch(x + (r + rstep) * xs, D, lane);
+      RowIO<T, VEC, PL>::prefetch(dy + (r + rstep) * dys, D, lane);
+    }
     RowIO<T, VEC, PL>::load(x + r * xs, D, lane, xv);
     RowIO<T, VEC, PL>::load(dy + r * dys, D, lane, g);
     const float mean = RMS ? 0.f : mean_in[r];
@@ -271,10 +289,17 @@ __global__ void __launch_bounds__(kNormThreads) nmd_fwd_kernel(const T* __restri
   const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   const uint32_t thr = dropout_threshold(p);
   const long long n_vec = n_rows * G;
-  for (long long vi = (long long)blockIdx.x * kNormWarps + warp; vi < n_vec; vi += (long long)gridDim.x * kNormWarps) {
+  const long long vstep = (long long)gridDim.x * kNormWarps;
+  for (long long vi = (long long)blockIdx.x * kNormWarps + warp; vi < n_vec; vi += vstep) {
     const long long r = vi / G;
     const int gidx = (int)(vi - r * G);
     float a[PL], uu[PL];
+    if (vi + vstep < n_vec) {
+      const long long r2 = (vi + vstep) / G;
+      const int g2 = (int)(vi + vstep - r2 * G);
+      RowIO<T, VEC, PL>::prefetch(attn + r2 * as + g2 * len, len, lane);
+      RowIO<T, VEC, PL>::prefetch(u + r2 * us + g2 * len, len, lane);
+    }
     RowIO<T, VEC, PL>::load(attn + r * as + gidx * len, len, lane, a);
     RowIO<T, VEC, PL>::load(u + r * us + gidx * len, len, lane, uu);
     float s = 0.f;
@@ -351,10 +376,23 @@ __global__ void __launch_bounds__(kNormThreads) nmd_bwd_kernel(
   const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   const uint32_t thr = dropout_threshold(p);
   const long long n_vec = n_rows * G;
-  for (long long vi = (long long)blockIdx.x * kNormWarps + warp; vi < n_vec; vi += (long long)gridDim.x * kNormWarps) {
+  const long long vstep = (long long)gridDim.x * kNormWarps;
+  for (long long vi = (long long)blockIdx.x * kNormWarps + warp; vi < n_vec; vi += vstep) {
     const long long r = vi / G;
     const int gidx = (int)(vi - r * G);
     float a[PL], uu[PL], gy[PL], gu[PL], ga[PL];
+    if (vi + vstep < n_vec) {
+      const long long r2 = (vi + vstep) / G;
+      const int g2 = (int)(vi + vstep - r2 * G);
+      RowIO<T, VEC, PL>::prefetch(attn + r2 * as + g2 * len, len, lane);
+      RowIO<T, VEC, PL>::prefetch(u + r2 * us + g2 * len, len, lane);
+      const T* d2 = dout + r2 * os + g2 * len;
+      RowIO<T, VEC, PL>::prefetch(d2, len, lane);
+      if (concat) {
+        RowIO<T, VEC, PL>::prefetch(d2 + width, len, lane);
+        RowIO<T, VEC, PL>::prefetch(d2 + 2 * width, len, lane);
+      }
+    }
     RowIO<T, VEC, PL>::load(attn + r * as + gidx * len, len, lane, a);
     RowIO<T, VEC, PL>::load(u + r * us + gidx * len, len, lane, uu);
     const T* drow = dout + r * os + gidx * len;

@@ -1,4 +1,5 @@
-// On-device self test of the tcgen05 / TMA building blocks (exported as hstu_umma_selftest).
+// On-device self test of the tcgen05 / TMA building blocks: libhstu_b200_selftest.so (include/hstu_b200_selftest.h), a TEST
+// library of its own -- nothing of this file is linked into the product library.
 //
 // One small GEMM kernel  D[128, N] = A[128, K] * B[N, K]^T  exercises, with exactly-representable integer data,
 // every operand layout the attention kernels rely on:
@@ -17,6 +18,8 @@
 #include "common.cuh"
 #include "internal.h"
 #include "umma.cuh"
+
+extern "C" const char* hstu_selftest_last_error(void);
 
 namespace hstu {
 using namespace umma;
@@ -460,7 +463,7 @@ static int run_gemm_case(const char* name, StCfg cfg, char* report, size_t cap) 
   else rc |= make_tmap_rows_heads(&tB, dB, N, 1, K, K, K, cfg.sw_b / 2, N);
   int fails = 0;
   if (rc != 0) {
-    rep(report, cap, "%-34s TENSORMAP-ERROR %s\n", name, hstu_last_error());
+    rep(report, cap, "%-34s TENSORMAP-ERROR %s\n", name, hstu_selftest_last_error());
     fails = 1;
   } else {
     const size_t smem = 1024 + 65536 + 65536;
@@ -512,7 +515,7 @@ static void mufu_case(const char* name, int per_iter, char* report, size_t cap) 
   cudaEventDestroy(e1);
 }
 
-int umma_selftest(char* report, size_t cap) {
+static int umma_selftest(char* report, size_t cap) {
   if (report == nullptr || cap < 64) return -1;
   report[0] = 0;
   int dev = 0;
@@ -619,3 +622,19 @@ int umma_selftest(char* report, size_t cap) {
 }
 
 }  // namespace hstu
+
+// ---- the test library's own C ABI and the one internal symbol tmap.cu needs ----
+namespace hstu {
+static thread_local char g_selftest_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_selftest_err, sizeof(g_selftest_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace hstu
+
+extern "C" {
+const char* hstu_selftest_last_error(void) { return hstu::g_selftest_err; }
+int hstu_umma_selftest(char* report, size_t report_bytes) { return hstu::umma_selftest(report, report_bytes); }
+}

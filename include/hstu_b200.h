@@ -249,11 +249,6 @@ typedef struct hstu_ssl_params {
 int hstu_sampled_softmax_fwd(const hstu_ssl_params* p, void* cuda_stream);
 int hstu_sampled_softmax_bwd(const hstu_ssl_params* p, void* cuda_stream);
 
-/* On-device self test of the tcgen05 / TMA primitives the attention kernels are built from (K-major and MN-major
- * shared-memory descriptors, TMEM load/store).  Writes a report into `report` (host buffer).  Returns the number
- * of failed checks (0 = all good, <0 = could not run).                                                       */
-int hstu_umma_selftest(char* report, size_t report_bytes);
-
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,7 @@ import ctypes as C, sys
 sys.path.insert(0, '.')
 from generative_recommenders_b200 import _lib
 buf = C.create_string_buffer(1 << 16)
-rc = _lib.lib().hstu_umma_selftest(buf, len(buf))
+rc = _lib.selftest_lib().hstu_umma_selftest(buf, len(buf))
 print(buf.value.decode()[-1500:])
 print('rc', rc)
 PY

@@ -14,7 +14,7 @@ def test_umma_selftest_report():
     from generative_recommenders_b200 import _lib
 
     buf = C.create_string_buffer(1 << 16)
-    fails = _lib.lib().hstu_umma_selftest(buf, len(buf))
+    fails = _lib.selftest_lib().hstu_umma_selftest(buf, len(buf))
     report = buf.value.decode()
     print(report)
     import os
