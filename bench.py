@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "triton"])
-    ap.add_argument("--workload", default="hstu_large", choices=["hstu_large", "attn"])
+    ap.add_argument("--workload", default="hstu_large", choices=["hstu_large", "attn", "ml20m", "amzn_books"])
     ap.add_argument("--batch", type=int, default=16, help="user sequences per GPU per step")
     ap.add_argument("--lmax", type=int, default=8192)
     ap.add_argument("--layers", type=int, default=16)
@@ -359,6 +359,105 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# research-path configs of BASELINE.json (2: ML-20M HSTU-large, 3: Amazon-Books HSTU-large): item embedding -> 16 research
+# blocks (relative position / time bias attention) -> sampled-softmax loss -> backward -> AdamW, synthetic data
+# ----------------------------------------------------------------------------------------------------------------
+RESEARCH_CFG = {
+    # configs/ml-20m/hstu-sampled-softmax-n128-large-final.gin, configs/amzn-books/hstu-sampled-softmax-n512-large-final.gin
+    # (SURVEY.md section 8 table): D, layers, H, dqk = dv, n = max_sequence_length + gr_output_length + 1, batch, negatives, items
+    "ml20m": dict(D=256, layers=16, H=8, d=32, n=211, B=128, R=128, V=131263, name="ML-20M HSTU-large"),
+    "amzn_books": dict(D=64, layers=16, H=8, d=8, n=61, B=128, R=512, V=695763, name="Amazon-Books HSTU-large"),
+}
+
+
+def run_research(args):
+    from generative_recommenders_b200 import _lib
+    from generative_recommenders_b200.build import build
+    from generative_recommenders_b200.modules.research_hstu import (RelativeBucketedTimeAndPositionBasedBias,
+                                                                    SequentialTransductionUnitJagged)
+    from generative_recommenders_b200.modules.sampled_softmax import LocalNegativesSampler, SampledSoftmaxLoss
+
+    c = RESEARCH_CFG[args.workload]
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    build()
+    _lib.lib()
+    torch.manual_seed(7)
+    D, H, d, n, B, R, V = c["D"], c["H"], c["d"], c["n"], c["B"], c["R"], c["V"]
+    emb = torch.nn.Embedding(V, D)
+    blocks = torch.nn.ModuleList([
+        SequentialTransductionUnitJagged(embedding_dim=D, linear_hidden_dim=d, attention_dim=d, dropout_ratio=0.2,
+                                         attn_dropout_ratio=0.0, num_heads=H, linear_activation="silu",
+                                         relative_attention_bias_module=RelativeBucketedTimeAndPositionBasedBias(n, 128),
+                                         normalization="rel_bias", linear_config="uvqk", concat_ua=False, epsilon=1e-6, max_length=n)
+        for _ in range(c["layers"])])
+    model = torch.nn.ModuleDict({"emb": emb, "blocks": blocks}).to(dev).to(torch.bfloat16)
+    sampler = LocalNegativesSampler(V, model["emb"], list(range(V)), l2_norm=True, l2_norm_eps=1e-6).to(dev)
+    loss_mod = SampledSoftmaxLoss(num_to_sample=R, softmax_temperature=0.05)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    g = torch.Generator(device="cpu").manual_seed(1001)
+    lengths = torch.randint(n // 2, n + 1, (B,), generator=g)
+    off = torch.zeros(B + 1, dtype=torch.int64)
+    off[1:] = torch.cumsum(lengths, 0)
+    L = int(off[-1])
+    ids_host = torch.randint(1, V, (L,), generator=g).pin_memory()
+    ts_host = torch.cumsum(torch.randint(0, 86400, (B, n), generator=g), dim=1).pin_memory()
+    off_d = off.to(dev)
+    mask = torch.tril(torch.ones(n, n, device=dev))
+    ids_dev, ts_dev = ids_host.to(dev), ts_host.to(dev)
+    nxt = torch.arange(1, L + 1, device=dev).clamp(max=L - 1)  # next-item supervision inside the flat row order (synthetic)
+    w_dev = torch.ones(L, device=dev, dtype=torch.bfloat16)
+
+    def step(e2e):
+        ids = ids_host.to(dev, non_blocking=True) if e2e else ids_dev
+        ts = ts_host.to(dev, non_blocking=True) if e2e else ts_dev
+        opt.zero_grad(set_to_none=True)
+        x = model["emb"](ids)
+        for blk in model["blocks"]:
+            x, _ = blk(x, off_d, ts, mask)
+        sup_ids = ids[nxt]
+        loss, _ = loss_mod.jagged_forward(output_embeddings=x, supervision_ids=sup_ids, supervision_embeddings=model["emb"](sup_ids),
+                                          supervision_weights=w_dev, negatives_sampler=sampler)
+        loss.backward()
+        opt.step()
+        return float(loss.item()) if e2e else loss
+
+    def timed(e2e, steps, warmup, with_events):
+        for _ in range(warmup):
+            step(e2e)
+        torch.cuda.synchronize(dev)
+        _lib.enable_timing(with_events)
+        l0 = _lib.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(e2e)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ev = _lib.timed_events()
+        _lib.enable_timing(False)
+        return e0.elapsed_time(e1), _lib.LAUNCHES - l0, ev
+
+    sampler_c = ClockSampler(dev.index or 0)
+    sampler_c.start()
+    ms, launches, events = timed(False, args.steps, args.warmup, True)
+    clocks = sampler_c.stop()
+    ms_e2e, _, _ = timed(True, args.steps, 1, False)
+    kt = {k: round(sum(a.elapsed_time(b) for a, b in v) / max(1, len(v)), 4) for k, v in (events or {}).items()}
+    print(json.dumps({
+        "metric": f"user-seqs/sec {c['name']} (research path) fwd+bwd+AdamW", "value": B * args.steps / (ms * 1e-3), "unit": "sequences/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{c['name']}: item embedding ({V} x {D}) -> {c['layers']} research HSTU blocks (D={D}, H={H}, dqk=dv={d}, "
+                               f"n={n}, relative position + time bias) -> sampled softmax ({R} negatives, l2 norm, T=0.05), batch {B}, "
+                               f"{L} rows, dropout 0.2, bf16", "global_batch": B, "seq_len": n, "rows_per_gpu": L,
+                   "l2": "the whole working set fits the 126 MB L2 except the embedding table; launch-bound at this size"},
+        "e2e": {"value": B * args.steps / (ms_e2e * 1e-3), "unit": "sequences/s", "h2d_bytes_per_step": ids_host.numel() * 8 + ts_host.numel() * 8,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "kernel_ms_per_call": kt}))
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # GPU comparator: the reference's own Triton kernel (unmodified, from baseline/_ref) on the same inputs
 # ----------------------------------------------------------------------------------------------------------------
 def run_triton(args):
@@ -630,5 +729,7 @@ if __name__ == "__main__":
         run_reference(a)
     elif a.impl == "triton":
         run_triton(a)
+    elif a.workload in RESEARCH_CFG:
+        run_research(a)
     else:
         run_ours(a)
