@@ -67,6 +67,12 @@ __device__ __forceinline__ SeqGeom seq_geom(const hstu_attn_params& p, int b) {
   return g;
 }
 
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 __device__ __forceinline__ float bias_at(const hstu_attn_params& p, int b, int i, int j) {
   // research/modeling/sequential/hstu.py:124-143
   float bias = 0.f;
@@ -355,6 +361,11 @@ __global__ void __launch_bounds__(256) attn_bwd_q_generic_kernel(const GenericAr
   float* sK = sDO + TILE * pv;
   float* sV = sK + TILE * pq;
   float* sDS = sV + TILE * pv;
+  float* hpos = sDS + TILE * pp;   // [2 TILE - 1] position-bias gradient of the current tile pair
+  float* hts = hpos + 2 * TILE;    // [num_ts_buckets + 1] time-bias gradient of this CTA
+  if (p.dpos_w || p.dts_w) {
+    for (int t = tid; t < 2 * TILE + (p.dts_w ? p.num_ts_buckets + 1 : 0); t += 256) hpos[t] = 0.f;
+  }
 
   const SeqMask msk = make_seq_mask(g.len, g.n_tgt, p.max_attn_len, p.min_full_attn_seq_len, p.contextual_seq_len);
   const int mrows = min(TILE, g.len - m0);
@@ -413,24 +424,47 @@ __global__ void __launch_bounds__(256) attn_bwd_q_generic_kernel(const GenericAr
         const int il = ty * R + r, jl = tx + 16 * c;
         const int i = m0 + il, j = n0 + jl;
         float ds = 0.f;
+        int bk = -1;
         if (il < mrows && jl < nrows && mask_valid(msk, i, j)) {
           float x = s[r][c] * p.alpha;
-          if (has_bias) x += bias_at(p, b, i, j);
-          const float sg = sigmoid_f(x);
-          ds = dp[r][c] * sg * (1.f + x * (1.f - sg)) * inv_n;
-          if (has_bias && ds != 0.f) {
+          if (has_bias) {
             const int n = p.max_seq_len;
-            if (p.dpos_w) atomicAdd(p.dpos_w + (n - 1 + j - i), ds);
-            if (p.dts_w) {
+            if (p.pos_w) x += p.pos_w[n - 1 + j - i];
+            if (p.ts_w) {
               const long long* ts = reinterpret_cast<const long long*>(p.timestamps) + (long long)b * n;
               const int i1 = i + 1 < n ? i + 1 : n - 1;
-              atomicAdd(p.dts_w + ts_bucket(ts[i1] - ts[j], p.num_ts_buckets), ds);
+              bk = ts_bucket(ts[i1] - ts[j], p.num_ts_buckets);
+              x += p.ts_w[bk];
+            }
+          }
+          const float sg = sigmoid_f(x);
+          ds = dp[r][c] * sg * (1.f + x * (1.f - sg)) * inv_n;
+        }
+        if (has_bias) {  // CTA-uniform
+          // The bias parameters are shared by every (sequence, head, i, j): one global atomic per score serialises on a few
+          // hundred addresses (10.8 ms per call at the ML-20M shape).  Gradients are first accumulated in shared memory --
+          // position bias: the 2 TILE - 1 diagonals of this tile pair (<= 2 lanes of a warp share one); time bias: lanes of
+          // a warp mostly hit ONE bucket, so the warp sums first -- and flushed with one global atomic per bin.
+          if (p.dpos_w && ds != 0.f) atomicAdd(hpos + (jl - il + TILE - 1), ds);
+          if (p.dts_w) {
+            int same;
+            __match_all_sync(0xffffffffu, bk, &same);
+            if (same) {
+              const float t = warp_sum_f(ds);
+              if ((tid & 31) == 0 && bk >= 0 && t != 0.f) atomicAdd(hts + bk, t);
+            } else if (bk >= 0 && ds != 0.f) {
+              atomicAdd(hts + bk, ds);
             }
           }
         }
         sDS[il * pp + jl] = ds;
       }
     __syncthreads();
+    if (has_bias && p.dpos_w && tid < 2 * TILE - 1) {
+      const float v = hpos[tid];
+      hpos[tid] = 0.f;  // the next tile pair accumulates after two more barriers
+      if (v != 0.f) atomicAdd(p.dpos_w + (p.max_seq_len - 1 + (n0 - m0) + tid - (TILE - 1)), v);
+    }
     for (int j = 0; j < nrows; ++j) {
       float dsr[R];
 #pragma unroll
@@ -444,6 +478,13 @@ __global__ void __launch_bounds__(256) attn_bwd_q_generic_kernel(const GenericAr
           for (int r = 0; r < R; ++r) adq[r][c] = fmaf(dsr[r], kk, adq[r][c]);
         }
       }
+    }
+  }
+  if (p.dts_w) {
+    __syncthreads();
+    for (int t = tid; t <= p.num_ts_buckets; t += 256) {
+      const float v = hts[t];
+      if (v != 0.f) atomicAdd(p.dts_w + t, v);
     }
   }
   T* dqp = reinterpret_cast<T*>(p.dq) + (g.q_row0 + m0) * p.dq_row_stride + (long long)h * p.dq_head_stride;
@@ -494,7 +535,8 @@ static int launch_bwd(const hstu_attn_params& p, cudaStream_t st) {
     HSTU_CUDA_OK(cudaGetLastError());
   }
   {
-    size_t smem = sizeof(float) * (size_t)(2 * TILE * (p.dqk + 1) + 2 * TILE * (p.dv + 1) + TILE * (TILE + 1));
+    size_t smem = sizeof(float) * (size_t)(2 * TILE * (p.dqk + 1) + 2 * TILE * (p.dv + 1) + TILE * (TILE + 1) + 2 * TILE +
+                                           (p.dts_w ? p.num_ts_buckets + 1 : 0));
     auto kern = attn_bwd_q_generic_kernel<T, TILE, DMAX>;
     if (int e = set_smem(kern, smem)) return e;
     kern<<<grid, 256, smem, st>>>(a);
