@@ -10,7 +10,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhstu_b200.so")
+# HSTU_B200_LIB: another build of the same ABI (compile-time variants for A/B measurements, scripts/build_variant.py)
+LIB_PATH = os.environ.get("HSTU_B200_LIB") or os.path.join(_HERE, "lib", "libhstu_b200.so")
 
 ABI_VERSION = 1
 F32, BF16, F16 = 0, 1, 2

@@ -44,8 +44,10 @@ def is_fresh() -> bool:
     return all(os.path.exists(p) and os.path.getmtime(p) >= _deps_mtime() for p in (LIB, SELFTEST_LIB))
 
 
-def _compile(src: str, extra) -> str:
+def _compile(src: str, extra, reuse: bool = False) -> str:
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+    if reuse and os.path.exists(obj):
+        return obj
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     hdrs.append(os.path.join(ROOT, "include", "hstu_b200.h"))
     newest = max(os.path.getmtime(p) for p in hdrs + [os.path.join(CSRC, src), __file__])
@@ -65,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    if force:
+    if force and not os.environ.get("HSTU_EXP_SRC"):
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
     extra = ["-Xptxas", "-v"] if verbose else []
@@ -74,8 +76,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for flag in os.environ.get("HSTU_EXP", "").split():
         extra.append("-D" + flag)
     all_src = list(dict.fromkeys(SOURCES + SELFTEST_SOURCES))
+    # HSTU_EXP_SRC="norm.cu,...": an experiment that touches only these units -- recompile them with the HSTU_EXP defines and
+    # link against the existing objects of everything else (A/B runs on the GPU box without a two-minute full rebuild)
+    only = [t for t in os.environ.get("HSTU_EXP_SRC", "").split(",") if t]
+    for t in only:
+        o = os.path.join(OBJ, t.replace(".cu", ".o"))
+        if os.path.exists(o):
+            os.remove(o)
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(all_src))) as ex:
-        objs = dict(zip(all_src, ex.map(lambda s: _compile(s, extra), all_src)))
+        objs = dict(zip(all_src, ex.map(lambda s: _compile(s, extra if (not only or s in only) else [], reuse=bool(only) and s not in only),
+                                        all_src)))
     for lib, srcs in ((LIB, SOURCES), (SELFTEST_LIB, SELFTEST_SOURCES)):
         cmd = [_nvcc(), "-shared", "-o", lib] + [objs[s] for s in srcs] + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -48,6 +48,9 @@ struct RowIO {
   // L2 prefetch of the lane's part of a row (the row a warp will process in its NEXT iteration): a warp works on one row at a
   // time, so without it only one row of loads per warp is in flight and the kernels are bound by HBM latency, not bandwidth
   static __device__ __forceinline__ void prefetch(const T* row, int D, int lane) {
+#ifdef HSTU_NORM_NO_PREFETCH
+    return;
+#endif
     if constexpr (VEC > 1) {
 #pragma unroll
       for (int k = 0; k < PL / VEC; ++k) {
