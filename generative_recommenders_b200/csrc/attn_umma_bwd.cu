@@ -609,6 +609,40 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
       const uint32_t st_addr = tmem + Cfg::TMEM_SLOT + slot * 128 + lane_bits;   // the slot holds one half-tile {S^T | dP^T}
       const uint32_t dp_addr = st_addr + 64;
+#ifdef HSTU_BWD_PRING_NOPF
+      if (Cfg::PRING) {
+        // PRING without the register-hungry prefetch: the chunk loop of the ring path (64 live inputs), the slot goes back to the
+        // score issuer as soon as the SECOND chunk is in registers, P^T goes to its own ring
+        const uint32_t p_addr = tmem + Cfg::TMEM_P + (u % Cfg::NPR) * 32 + lane_bits;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t s[32], dp[32];
+          tmem_ld32(st_addr + c * 32, s);
+          tmem_ld32(dp_addr + c * 32, dp);
+          tmem_ld_wait();
+          if (c == 1) {
+            tc_fence_before_sync();
+            mbar_arrive(&bars->scores_free[wg]);
+          } else {
+            if (i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);
+            if (u >= Cfg::NPR) {
+              mbar_wait(&bars->p_free[u % Cfg::NPR], ((u / Cfg::NPR) - 1) & 1);
+              tc_fence_after_sync();
+            }
+          }
+          uint32_t pp[16], dd[16];
+#define HSTU_S32(e) s[e]
+#define HSTU_D32(e) dp[e]
+          HSTU_BWD_RUN(32, HSTU_S32, HSTU_D32, pp, dd, c * 32);
+#undef HSTU_S32
+#undef HSTU_D32
+          tmem_st16(p_addr + c * 16, pp);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + j4), dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
+        }
+      } else
+#endif
       if (Cfg::PRING) {
         // Two chunks of 32 query columns; the second is loaded while the first is processed, and as soon as it has landed the
         // slot goes back to the issuer (scores_free): the score GEMMs of this warpgroup's next unit run during the second half

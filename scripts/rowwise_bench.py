@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--sets", type=int, default=4)
     ap.add_argument("--only", default="")
+    ap.add_argument("--profile", action="store_true", help="one launch per kernel, no warm-up (for ncu)")
     args = ap.parse_args()
     from generative_recommenders_b200 import _lib
     from generative_recommenders_b200.build import build
@@ -62,6 +63,9 @@ def main():
     out = {"rows": L, "D": D, "hbm_peak_gbs": peak, "kernels": {}}
     for name, (bytes_per_row, fn) in cases.items():
         if only and name not in only:
+            continue
+        if args.profile:
+            fn(0)
             continue
         for i in range(3):
             fn(i % S)
