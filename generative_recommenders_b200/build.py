@@ -21,7 +21,7 @@ LIB = os.path.join(HERE, "lib", "libhstu_b200.so")
 SELFTEST_LIB = os.path.join(HERE, "lib", "libhstu_b200_selftest.so")  # test infrastructure: tcgen05 / TMA self test + micro-benchmarks
 
 SELFTEST_SOURCES = ["umma_selftest.cu", "tmap.cu"]
-SOURCES = ["api.cu", "attn_generic.cu", "attn_umma_fwd.cu", "attn_umma_bwd.cu", "tmap.cu", "norm.cu", "jagged.cu", "position.cu", "sampled_softmax.cu", "jagged_bmm.cu"]
+SOURCES = ["api.cu", "attn_generic.cu", "attn_umma_fwd.cu", "attn_umma_bwd.cu", "tmap.cu", "norm.cu", "norm_fast.cu", "jagged.cu", "position.cu", "sampled_softmax.cu", "jagged_bmm.cu"]
 NVCC_FLAGS = [
     "-std=c++20", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcudafe", "--diag_suppress=177",

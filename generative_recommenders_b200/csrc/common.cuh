@@ -176,8 +176,10 @@ __device__ __forceinline__ void zero_rows(void* base, int elem_bytes, long long 
   }
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// MUFU.EX2 + MUFU.RCP (2 ulp): the IEEE division `1.0f / x` compiles to ~15 instructions with a slow-path call, which made the
+// SiLU kernels issue-bound (26 instructions per element)
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 
 // time-bucket of the research relative bias: clamp(floor(log(max(|d|,1))/0.301), 0, nb)  (hstu.py:604-612)
 __device__ __forceinline__ int ts_bucket(long long d, int nb) {

@@ -11,6 +11,20 @@
 
 namespace hstu {
 
+// norm_fast.cu: the same kernels specialised for 16-bit elements and a normalised length of 256 (no predicates, packed math)
+bool norm_fast_applicable(int dtype, int len);
+int layer_norm_fwd_fast(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, long long n, long long xs,
+                        long long ys, float eps, int dtype, cudaStream_t st);
+int layer_norm_bwd_fast(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx, float* partial,
+                        long long n, long long xs, long long dys, long long dxs, int dtype, int* grid_out, cudaStream_t st);
+int norm_mul_dropout_fwd_fast(const void* attn, const void* u, const void* w, const void* b, void* out, float* mean, float* rstd,
+                              long long n, long long as, long long us, float eps, float p, unsigned long long seed, int dtype,
+                              int silu_u, int concat, cudaStream_t st);
+int norm_mul_dropout_bwd_fast(const void* dout, const void* attn, const void* u, const void* w, const void* b, const float* mean,
+                              const float* rstd, void* dattn, void* du, float* partial, long long n, long long as, long long us,
+                              long long das, long long dus, float p, unsigned long long seed, int dtype, int silu_u, int concat,
+                              int* grid_out, cudaStream_t st);
+
 constexpr int kNormThreads = 256;
 constexpr int kNormWarps = kNormThreads / 32;
 constexpr int kMaxPerLane = 32;     // 32 lanes * 32 = 1024 elements per normalised vector
@@ -511,31 +525,50 @@ __global__ void __launch_bounds__(kNormThreads) nmd_bwd_kernel(
 template <typename T, int VEC, bool BWD>
 __global__ void silu_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, long long n_rows,
                             int n_cols, long long xs, long long dys, long long os) {
+  // U independent 16-byte vectors per thread and iteration: all loads are issued before the first use, so that a thread has
+  // U (forward) or 2 U (backward) requests in flight -- with one, 64 resident warps cover only half of the bandwidth-delay product
+  constexpr int U = VEC == 1 ? 1 : 4;
   const int vec_per_row = n_cols / VEC;
   const long long total = n_rows * vec_per_row;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long r = idx / vec_per_row;
-    const int c = (int)(idx - r * vec_per_row) * VEC;
-    T xv[VEC], gv[VEC], ov[VEC];
-    if constexpr (VEC == 1) {
-      xv[0] = x[r * xs + c];
-      if (BWD) gv[0] = dy[r * dys + c];
-    } else {
-      *reinterpret_cast<uint4*>(xv) = *reinterpret_cast<const uint4*>(x + r * xs + c);
-      if (BWD) *reinterpret_cast<uint4*>(gv) = *reinterpret_cast<const uint4*>(dy + r * dys + c);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += stride * U) {
+    T xv[U][VEC], gv[U][VEC];
+    long long xo[U], oo[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long long idx = idx0 + k * stride;
+      if (idx < total) {
+        const long long r = idx / vec_per_row;
+        const int c = (int)(idx - r * vec_per_row) * VEC;
+        xo[k] = r * xs + c;
+        oo[k] = r * os + c;
+        if constexpr (VEC == 1) {
+          xv[k][0] = x[xo[k]];
+          if (BWD) gv[k][0] = dy[r * dys + c];
+        } else {
+          *reinterpret_cast<uint4*>(xv[k]) = *reinterpret_cast<const uint4*>(x + xo[k]);
+          if (BWD) *reinterpret_cast<uint4*>(gv[k]) = *reinterpret_cast<const uint4*>(dy + r * dys + c);
+        }
+      }
     }
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const float xf = Cvt<T>::to_f(xv[i]);
-      const float sg = sigmoid_f(xf);
-      float o = xf * sg;
-      if (BWD) o = Cvt<T>::to_f(gv[i]) * sg * (1.f + xf * (1.f - sg));
-      ov[i] = Cvt<T>::from_f(o);
-    }
-    if constexpr (VEC == 1) {
-      out[r * os + c] = ov[0];
-    } else {
-      *reinterpret_cast<uint4*>(out + r * os + c) = *reinterpret_cast<const uint4*>(ov);
+    for (int k = 0; k < U; ++k) {
+      if (idx0 + k * stride < total) {
+        T ov[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float xf = Cvt<T>::to_f(xv[k][i]);
+          const float sg = sigmoid_f(xf);
+          float o = xf * sg;
+          if (BWD) o = Cvt<T>::to_f(gv[k][i]) * sg * (1.f + xf * (1.f - sg));
+          ov[i] = Cvt<T>::from_f(o);
+        }
+        if constexpr (VEC == 1) {
+          out[oo[k]] = ov[0];
+        } else {
+          *reinterpret_cast<uint4*>(out + oo[k]) = *reinterpret_cast<const uint4*>(ov);
+        }
+      }
     }
   }
 }
@@ -550,6 +583,18 @@ static inline int norm_grid(long long n_vec, bool fwd = false) {
   if (need < 1) need = 1;
   const int cap = fwd ? kFwdGridCap : kPartialRows;
   return (int)(need < cap ? need : cap);
+}
+
+// 16-bit elements: every pointer 16-byte aligned, every row stride a multiple of 8 elements
+static bool fast_layout(std::initializer_list<const void*> ptrs, std::initializer_list<long long> strides) {
+#ifdef HSTU_NORM_NO_FAST
+  return false;
+#endif
+  for (const void* p : ptrs)
+    if (p == nullptr || !aligned16(p)) return false;
+  for (long long s : strides)
+    if (s % 8) return false;
+  return true;
 }
 
 template <typename T>
@@ -638,6 +683,8 @@ int layer_norm_fwd(const void* x, const void* w, const void* b, void* y, float* 
     set_error("layer_norm: D=%d outside the supported range [1, %d]", D, 32 * kMaxPerLane);
     return HSTU_ERR_UNSUPPORTED;
   }
+  if (norm_fast_applicable(dtype, D) && !swish && !rms && fast_layout({x, w, b, y}, {xs, ys}))
+    return layer_norm_fwd_fast(x, w, b, y, mean, rstd, n, xs, ys, eps, dtype, st);
   DISPATCH_DTYPE(dtype, (ln_fwd_t<T>(x, w, b, y, mean, rstd, n, D, xs, ys, eps, swish, rms, st)));
 }
 
@@ -651,6 +698,21 @@ int layer_norm_bwd(const void* dy, const void* x, const void* w, const void* b, 
   if (n == 0) {
     if (dw) HSTU_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * D, st));
     if (db) HSTU_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * D, st));
+    return 0;
+  }
+  if (norm_fast_applicable(dtype, D) && !swish && !rms && fast_layout({dy, x, w, b, dx}, {xs, dys, dxs})) {
+    const bool want_param = (dw != nullptr || db != nullptr);
+    if (want_param && partial == nullptr) {
+      set_error("layer_norm_bwd: dw/db requested but no partial scratch given");
+      return HSTU_ERR_WORKSPACE;
+    }
+    int grid = 0;
+    if (int rc = layer_norm_bwd_fast(dy, x, w, mean, rstd, dx, want_param ? partial : nullptr, n, xs, dys, dxs, dtype, &grid, st))
+      return rc;
+    if (want_param) {
+      colsum_kernel<<<(2 * D + 31) / 32, 32 * kColsumGroups, 0, st>>>(partial, grid, 2 * D, D, dw, db);
+      HSTU_CUDA_OK(cudaGetLastError());
+    }
     return 0;
   }
   DISPATCH_DTYPE(dtype, (ln_bwd_t<T>(dy, x, w, b, mean, rstd, dx, dw, db, partial, n, D, xs, dys, dxs, swish, rms, st)));
@@ -714,6 +776,8 @@ int norm_mul_dropout_fwd(const void* attn, const void* u, const void* w, const v
     set_error("norm_mul_dropout: normalised length %d outside [1, %d]", len, 32 * kMaxPerLane);
     return HSTU_ERR_UNSUPPORTED;
   }
+  if (!gn && norm_fast_applicable(dtype, len) && fast_layout({attn, u, w, b, out}, {as, us}))
+    return norm_mul_dropout_fwd_fast(attn, u, w, b, out, mean, rstd, n, as, us, eps, p, seed, dtype, silu_u, concat, st);
   DISPATCH_DTYPE(dtype, (nmd_fwd_t<T>(attn, u, w, b, out, mean, rstd, n, H, dv, as, us, eps, p, seed, silu_u, concat, gn, st)));
 }
 
@@ -733,6 +797,22 @@ int norm_mul_dropout_bwd(const void* dout, const void* attn, const void* u, cons
     if (db) HSTU_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * np, st));
     return 0;
   }
+  if (!gn && norm_fast_applicable(dtype, len) && fast_layout({dout, attn, u, w, b, dattn, du}, {as, us, das, dus})) {
+    const bool want_param = (dw != nullptr || db != nullptr);
+    if (want_param && partial == nullptr) {
+      set_error("norm_mul_dropout_bwd: dw/db requested but no partial scratch given");
+      return HSTU_ERR_WORKSPACE;
+    }
+    int grid = 0;
+    if (int rc = norm_mul_dropout_bwd_fast(dout, attn, u, w, b, mean, rstd, dattn, du, want_param ? partial : nullptr, n, as, us,
+                                           das, dus, p, seed, dtype, silu_u, concat, &grid, st))
+      return rc;
+    if (want_param) {
+      colsum_kernel<<<(2 * len + 31) / 32, 32 * kColsumGroups, 0, st>>>(partial, grid, 2 * len, len, dw, db);
+      HSTU_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+  }
   DISPATCH_DTYPE(dtype, (nmd_bwd_t<T>(dout, attn, u, w, b, mean, rstd, dattn, du, dw, db, partial, n, H, dv, as, us, das,
                                       dus, p, seed, silu_u, concat, gn, st)));
 }
@@ -743,8 +823,9 @@ static int silu_t(const void* x, const void* dy, void* out, long long n, int col
   constexpr int VEC = 16 / sizeof(T);
   const bool v = can_vec<T>(cols, {x, dy, out}, {xs, dys, os});
   const long long total = n * (cols / (v ? VEC : 1));
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  const int per_thread = v ? 4 : 1;  // the kernel's U
+  long long blocks = (total + 256 * per_thread - 1) / (256 * per_thread);
+  if (blocks > 148 * 8) blocks = 148 * 8;  // one resident wave
   if (blocks < 1) blocks = 1;
 #define LAUNCH(VV, BB) silu_kernel<T, VV, BB><<<(int)blocks, 256, 0, st>>>((const T*)x, (const T*)dy, (T*)out, n, cols, xs, dys, os)
   if (bwd) {
