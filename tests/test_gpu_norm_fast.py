@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import hstu_oracle as O
-from tests.util import assert_rel
+from util import assert_rel
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
