@@ -97,6 +97,16 @@ struct BwdCfg {
 #define HSTU_BWD_PRING_MASK 64   /* bit mask over head dims: 32 | 64 */
 #endif
   static constexpr bool PRING = (HSTU_BWD_PRING_MASK & D) != 0 && D <= 64;
+  // ACC16: the score GEMMs S^T = K Q^T and dP^T = V dO^T accumulate in fp16 (c_format = F16): a half-tile of 64 values takes 32
+  // TMEM columns instead of 64, so the elementwise warpgroups read HALF the bytes through tcgen05.ld (the TMEM read port, 64 B /
+  // clk / SM, is what bounds the d = 32 kernel: S + dP + dQ = 144 KB per tile = 2300 clk, measured 2350-2450) and a slot is 64 columns.
+#ifdef HSTU_BWD_ACC16
+  static constexpr bool ACC16 = (D == 32);
+#else
+  static constexpr bool ACC16 = false;
+#endif
+  static constexpr int SLOT_COLS = ACC16 ? 64 : 128;   // {S^T half-tile | dP^T half-tile}
+  static constexpr int HALF_COLS = SLOT_COLS / 2;
   static constexpr int NSLOT = PRING ? 2 : (D <= 32 ? 3 : (D == 64 ? 2 : 1));
   static constexpr int NPR = (D <= 32) ? 4 : 2;  // PRING: P^T buffers (unit u -> u % NPR)
   static constexpr int NDQ = (D <= 32) ? 2 : ((D == 64 && !PRING) ? 2 : 1);
@@ -105,8 +115,8 @@ struct BwdCfg {
   static constexpr int NSF = NSLOT < 2 ? 2 : NSLOT;
   static constexpr int LAG = NDQ;                // the warpgroups drain dQ of tile i - LAG after their unit of tile i
   static constexpr int TMEM_SLOT = 0;
-  static constexpr int TMEM_P = NSLOT * 128;     // PRING: NPR buffers of 32 columns
-  static constexpr int TMEM_DV = NSLOT * 128 + (PRING ? NPR * 32 : 0);
+  static constexpr int TMEM_P = NSLOT * SLOT_COLS;     // PRING: NPR buffers of 32 columns
+  static constexpr int TMEM_DV = NSLOT * SLOT_COLS + (PRING ? NPR * 32 : 0);
   static constexpr int TMEM_DK = TMEM_DV + D;
   static constexpr int TMEM_DQ = TMEM_DK + D;   // NDQ buffers of D columns
   static_assert(TMEM_DQ + NDQ * D <= 512, "TMEM budget");
@@ -285,7 +295,8 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     const bool leader = lane == 0;
     const int U = 2 * T;
     if (warp == 0) {
-      constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, false, false);  // S^T, dP^T half-tiles (fp16 x fp16)
+      // S^T, dP^T half-tiles (fp16 x fp16); ACC16: fp16 accumulators (c_format bits [4, 6) = 0)
+      constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, false, false) & (Cfg::ACC16 ? ~(3u << 4) : ~0u);
       const uint64_t dk_k = desc_kmajor<SW>(smem_u32(sK), 0);                        // K as K-major A (S^T)
       const uint64_t dv_k = desc_kmajor<SW>(smem_u32(sV), 0);                        // V as K-major A (dP^T)
       const uint64_t dq_k = desc_kmajor<SW>(smem_u32(sQ), 0);                        // Q_i rows as K-major B
@@ -310,7 +321,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         }
         // query rows [64 hf, 64 hf + 64) of the staged Q_i / dO_i tiles
         const uint64_t row_off = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);
-        const uint32_t ts = tmem + Cfg::TMEM_SLOT + slot * 128;
+        const uint32_t ts = tmem + Cfg::TMEM_SLOT + slot * Cfg::SLOT_COLS;
         if (leader) {
           HSTU_TSTAMP(0, u, 1);
 #pragma unroll
@@ -323,7 +334,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
           for (int ks = 0; ks < D / 16; ++ks) {
             const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
             const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
-            mma_ss(ts + 64, dv_k + o, ddo_k + row_off + o, idesc_s, ks > 0);
+            mma_ss(ts + Cfg::HALF_COLS, dv_k + o, ddo_k + row_off + o, idesc_s, ks > 0);
           }
           mma_commit(&bars->s_full[u % Cfg::NSF]);
           HSTU_TSTAMP(0, u, 2);
@@ -343,7 +354,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         mbar_wait(&bars->unit_done[hf * 2 + pb], (i >> 1) & 1);
         tc_fence_after_sync();
         const uint64_t rows = (uint64_t)((st * Cfg::TILE_BYTES + hf * 64 * SW) >> 4);  // MN-major B: K rows = the 64 query rows
-        const uint32_t tp = Cfg::PRING ? tmem + Cfg::TMEM_P + (u % Cfg::NPR) * 32 : tmem + Cfg::TMEM_SLOT + slot * 128;
+        const uint32_t tp = Cfg::PRING ? tmem + Cfg::TMEM_P + (u % Cfg::NPR) * 32 : tmem + Cfg::TMEM_SLOT + slot * Cfg::SLOT_COLS;
         if (leader) {
           HSTU_TSTAMP(1, u, 1);
 #pragma unroll
@@ -607,8 +618,8 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + wg * 16384);
       const int jr = j_pos - m0 - cbase;           // query column (relative to this warpgroup's half) equal to j
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
-      const uint32_t st_addr = tmem + Cfg::TMEM_SLOT + slot * 128 + lane_bits;   // the slot holds one half-tile {S^T | dP^T}
-      const uint32_t dp_addr = st_addr + 64;
+      const uint32_t st_addr = tmem + Cfg::TMEM_SLOT + slot * Cfg::SLOT_COLS + lane_bits;   // the slot holds one half-tile {S^T | dP^T}
+      const uint32_t dp_addr = st_addr + Cfg::HALF_COLS;
 #ifdef HSTU_BWD_PRING_NOPF
       if (Cfg::PRING) {
         // PRING without the register-hungry prefetch: the chunk loop of the ring path (64 live inputs), the slot goes back to the
@@ -683,9 +694,26 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
 #pragma unroll
         for (int c = 0; c < 2; ++c) {  // 2 chunks of 32 query columns
           uint32_t s[32], dp[32];
-          tmem_ld32(st_addr + c * 32, s);
-          tmem_ld32(dp_addr + c * 32, dp);
-          tmem_ld_wait();
+          if constexpr (Cfg::ACC16) {
+            // fp16 accumulators: 32 values = 16 columns of packed pairs; widened to fp32 here (the arithmetic stays fp32)
+            uint32_t s16[16], dp16[16];
+            tmem_ld16(st_addr + c * 16, s16);
+            tmem_ld16(dp_addr + c * 16, dp16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float2 sf = __half22float2(*reinterpret_cast<const __half2*>(&s16[e]));
+              const float2 df = __half22float2(*reinterpret_cast<const __half2*>(&dp16[e]));
+              s[2 * e] = __float_as_uint(sf.x);
+              s[2 * e + 1] = __float_as_uint(sf.y);
+              dp[2 * e] = __float_as_uint(df.x);
+              dp[2 * e + 1] = __float_as_uint(df.y);
+            }
+          } else {
+            tmem_ld32(st_addr + c * 32, s);
+            tmem_ld32(dp_addr + c * 32, dp);
+            tmem_ld_wait();
+          }
           if (c == 0 && i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
           uint32_t pp[16], dd[16];
 #define HSTU_S32(e) s[e]

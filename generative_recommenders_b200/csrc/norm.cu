@@ -527,11 +527,14 @@ __global__ void silu_kernel(const T* __restrict__ x, const T* __restrict__ dy, T
                             int n_cols, long long xs, long long dys, long long os) {
   // U independent 16-byte vectors per thread and iteration: all loads are issued before the first use, so that a thread has
   // U (forward) or 2 U (backward) requests in flight -- with one, 64 resident warps cover only half of the bandwidth-delay product
-  constexpr int U = VEC == 1 ? 1 : 4;
+  constexpr int U = VEC == 1 ? 1 : (BWD ? 2 : 4);
   const int vec_per_row = n_cols / VEC;
   const long long total = n_rows * vec_per_row;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += stride * U) {
+  // a CTA works on contiguous chunks of U * blockDim vectors (thread t: vectors t, t + blockDim, ...): the U requests of a thread
+  // stay within a few KB of each other (DRAM page locality) instead of a whole grid stride apart
+  const long long stride = blockDim.x;
+  const long long chunk = (long long)blockDim.x * U;
+  for (long long idx0 = (long long)blockIdx.x * chunk + threadIdx.x; idx0 - threadIdx.x < total; idx0 += (long long)gridDim.x * chunk) {
     T xv[U][VEC], gv[U][VEC];
     long long xo[U], oo[U];
 #pragma unroll
@@ -823,7 +826,7 @@ static int silu_t(const void* x, const void* dy, void* out, long long n, int col
   constexpr int VEC = 16 / sizeof(T);
   const bool v = can_vec<T>(cols, {x, dy, out}, {xs, dys, os});
   const long long total = n * (cols / (v ? VEC : 1));
-  const int per_thread = v ? 4 : 1;  // the kernel's U
+  const int per_thread = v ? (bwd ? 2 : 4) : 1;  // the kernel's U
   long long blocks = (total + 256 * per_thread - 1) / (256 * per_thread);
   if (blocks > 148 * 8) blocks = 148 * 8;  // one resident wave
   if (blocks < 1) blocks = 1;

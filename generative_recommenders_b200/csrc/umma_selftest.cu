@@ -31,6 +31,7 @@ struct StCfg {
   int sw_a, sw_b;
   int variant;  // 1: swap LBO/SBO of MN-major descriptors (diagnostic)
   int a_f16;    // 1: A holds fp16 values while B stays bf16 (mixed operand formats of kind::f16: the fp16 P / dS operands)
+  int c_f16;    // 1: A and B fp16, accumulator fp16 (c_format = F16): N values packed into N / 2 TMEM columns
 };
 
 template <int SW>
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constan
   if (tid == 0) {
     mbar_wait(&bar_full, 0);
     tc_fence_after_sync();
-    const uint32_t idesc = make_idesc(M, N, cfg.a_mode == 1, cfg.b_mode == 1, cfg.a_f16 == 0, true);
+    uint32_t idesc = make_idesc(M, N, cfg.a_mode == 1, cfg.b_mode == 1, cfg.a_f16 == 0 && cfg.c_f16 == 0, cfg.c_f16 == 0);
+    if (cfg.c_f16) idesc &= ~(3u << 4);  // c_format = F16
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
     for (int k = 0; k < K / 16; ++k) {
       const uint64_t bd = op_desc_rt(cfg.sw_b, cfg.b_mode, b_base, cfg.b_mode == 1 ? K : N, k, cfg.variant);
@@ -153,6 +155,19 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constan
   }
   mbar_wait(&bar_mma, 0);
   tc_fence_after_sync();
+  if (cfg.c_f16) {
+    for (int c0 = 0; c0 < N / 2; c0 += 16) {  // fp16 accumulator: column c holds elements 2c (low half) and 2c + 1
+      uint32_t r[16];
+      tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const __half2 h2 = *reinterpret_cast<const __half2*>(&r[i]);
+        Dg[(size_t)tid * N + 2 * (c0 + i)] = __low2float(h2);
+        Dg[(size_t)tid * N + 2 * (c0 + i) + 1] = __high2float(h2);
+      }
+    }
+  } else
   for (int c0 = 0; c0 < N; c0 += 16) {
     uint32_t r[16];
     tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
@@ -307,6 +322,82 @@ __global__ void __launch_bounds__(128) umma_commit_kernel(int per_group, int nco
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// ---- TMEM read / write rate: `nwarps` warps (warp w reads the lane quarter w & 3) each issue `iters` x 4 tcgen05.ld 32x32b.x32
+// (4 KB per instruction) or tcgen05.st .x16, waiting once per group of four.  Reports bytes per clock of the whole SM. ----
+__global__ void __launch_bounds__(512) tmem_rate_kernel(int iters, int store, long long* out) {
+  __shared__ uint32_t tmem_base_s;
+  __shared__ long long t0s[16], t1s[16];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t base = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  uint32_t r[4][32];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[k][i] = tid + i;
+  __syncthreads();
+  const long long t0 = clock64();
+  if (!store) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tmem_ld32(base + ((it * 4 + k) * 32 & 511), r[k]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc += r[k][0] ^ r[k][31];
+    }
+  } else {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = r[k][i] + it;
+        tmem_st16(base + ((it * 4 + k) * 16 & 511), v);
+      }
+      tmem_st_wait();
+    }
+  }
+  const long long t1 = clock64();
+  if (lane == 0) {
+    t0s[warp] = t0;
+    t1s[warp] = t1;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    long long a = t0s[0], b = t1s[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      a = a < t0s[w] ? a : t0s[w];
+      b = b > t1s[w] ? b : t1s[w];
+    }
+    out[0] = b - a;
+    out[1] = acc;
+  }
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
+static void tmem_rate_case(int nwarps, int store, char* report, size_t cap) {
+  long long* d = nullptr;
+  long long h[2] = {0, 0};
+  const int iters = 2048;
+  cudaMalloc(&d, sizeof(h));
+  tmem_rate_kernel<<<1, nwarps * 32>>>(iters, store, d);
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    rep(report, cap, "tmem-rate/ CUDA-ERROR\n");
+    return;
+  }
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  const double bytes = (double)nwarps * iters * 4 * (store ? 2048.0 : 4096.0);
+  rep(report, cap, "tmem-rate/%s %2d warps: %7.1f B/clk per SM (%lld clk for %.0f KB)\n", store ? "tcgen05.st x16" : "tcgen05.ld x32",
+      nwarps, bytes / (double)h[0], h[0], bytes / 1024);
+}
+
 static void commit_case(int per_group, int ncommit, char* report, size_t cap) {
   long long* d = nullptr;
   long long h[2] = {0, 0};
@@ -437,13 +528,19 @@ static int run_gemm_case(const char* name, StCfg cfg, char* report, size_t cap) 
   // device storage: K-major operands as [rows][K]; MN-major operands as [K][rows]
   std::vector<__nv_bfloat16> dAh = hA, dBh = hB;
   if (cfg.a_mode == 1) for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) dAh[(size_t)k * M + m] = hA[(size_t)m * K + k];
-  if (cfg.a_f16) {  // same values, fp16 bit patterns (the tensor map / copies only move 16-bit words)
+  if (cfg.a_f16 || cfg.c_f16) {  // same values, fp16 bit patterns (the tensor map / copies only move 16-bit words)
     for (auto& x : dAh) {
       const __half hv = __float2half(__bfloat162float(x));
       memcpy((void*)&x, &hv, 2);
     }
   }
   if (cfg.b_mode == 1) for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) dBh[(size_t)k * N + n] = hB[(size_t)n * K + k];
+  if (cfg.c_f16) {
+    for (auto& x : dBh) {
+      const __half hv = __float2half(__bfloat162float(x));
+      memcpy((void*)&x, &hv, 2);
+    }
+  }
   __nv_bfloat16 *dA = nullptr, *dB = nullptr;
   float* dD = nullptr;
   int* dS = nullptr;
@@ -561,6 +658,23 @@ static int umma_selftest(char* report, size_t cap) {
       {"A f16 TMEM K128, B bf16 MN sw64",  {32, 128, 3, 1, 128, 64, 0, 1}},
       {"A f16 K sw128, B bf16 K sw128",    {128, 128, 0, 0, 128, 128, 0, 1}},
   };
+  // Probe (HSTU_SELFTEST_F16ACC=1, own process): fp16 accumulators
+  const Case f16acc_cases[] = {
+      // fp16 accumulators (c_format = F16): N values in N / 2 TMEM columns -- half the tcgen05.ld traffic of the score tiles
+      {"F16 acc: KK sw128 K128 N128",     {128, 128, 0, 0, 128, 128, 0, 0, 1}},
+      {"F16 acc: KK sw64 K32 N64",        {64, 32, 0, 0, 64, 64, 0, 0, 1}},
+      {"F16 acc: A TMEM K64, B MN N32",   {32, 64, 3, 1, 128, 64, 0, 0, 1}},
+  };
+  if (const char* env = getenv("HSTU_SELFTEST_F16ACC"); env && env[0] == '1') {
+    for (const Case& c : f16acc_cases) {
+      int r = run_gemm_case(c.name, c.cfg, report, cap);
+      if (r == -1000) {
+        rep(report, cap, "fp16 accumulator: rejected by the hardware (CUDA error above); probe ends here\n");
+        return 0;
+      }
+    }
+    return 0;
+  }
   if (const char* env = getenv("HSTU_SELFTEST_MIXED"); env && env[0] == '1') {
     for (const Case& c : mixed_cases) {
       int r = run_gemm_case(c.name, c.cfg, report, cap);
@@ -605,6 +719,8 @@ static int umma_selftest(char* report, size_t cap) {
   for (int w = 0; w < 2; ++w)
     for (int n = 1; n <= 3; ++n) multi_case(n, w, report, cap);
 
+  for (int nw : {1, 4, 8, 12, 16}) tmem_rate_case(nw, 0, report, cap);
+  for (int nw : {4, 8}) tmem_rate_case(nw, 1, report, cap);
   mufu_case<0>("tanh.approx.f32", 4, report, cap);
   mufu_case<1>("ex2+rcp f32 (sigmoid)", 2, report, cap);
   mufu_case<2>("tanh.approx.bf16x2", 4, report, cap);
