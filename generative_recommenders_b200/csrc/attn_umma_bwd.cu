@@ -53,6 +53,12 @@ struct alignas(64) BwdParams {
   float dk_scale;  // alpha / N
 };
 
+#ifdef HSTU_BWD_PSMEM
+constexpr bool kBwdPsmem = true;
+#else
+constexpr bool kBwdPsmem = false;
+#endif
+
 template <int D>
 struct BwdCfg {
   static constexpr int SW = (D * 2 >= 128) ? 128 : D * 2;
@@ -74,7 +80,8 @@ struct BwdCfg {
   static constexpr int DQ_NPASS = D / DQ_BOX_COLS;
   static constexpr int DQS_BYTES = 128 * DQ_BOX_COLS * 4;
   static constexpr int OFF_DQS = OFF_DST + 2 * PT_BYTES;
-  static constexpr int OFF_BAR = OFF_DQS + 2 * DQS_BYTES;
+  static constexpr int OFF_PT = OFF_DQS + 2 * DQS_BYTES;   // PSM: NPB P^T boxes [128 kv][64 q] fp16
+  static constexpr int OFF_BAR = OFF_PT + ((kBwdPsmem && D == 32) ? 3 * 16384 : 0);
   static_assert(OFF_BAR + 256 + 1024 <= 232448, "shared memory budget");
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   // TMEM: a ring of NSLOT score slots, each {S^T half-tile: 64 columns, dP^T half-tile: 64 columns} (a half-tile is
@@ -97,15 +104,20 @@ struct BwdCfg {
 #define HSTU_BWD_PRING_MASK 64   /* bit mask over head dims: 32 | 64 */
 #endif
   static constexpr bool PRING = (HSTU_BWD_PRING_MASK & D) != 0 && D <= 64;
-  // ACC16: the score GEMMs S^T = K Q^T and dP^T = V dO^T accumulate in fp16 (c_format = F16): a half-tile of 64 values takes 32
-  // TMEM columns instead of 64, so the elementwise warpgroups read HALF the bytes through tcgen05.ld (the TMEM read port, 64 B /
-  // clk / SM, is what bounds the d = 32 kernel: S + dP + dQ = 144 KB per tile = 2300 clk, measured 2350-2450) and a slot is 64 columns.
-#ifdef HSTU_BWD_ACC16
-  static constexpr bool ACC16 = (D == 32);
-#else
-  static constexpr bool ACC16 = false;
-#endif
-  static constexpr int SLOT_COLS = ACC16 ? 64 : 128;   // {S^T half-tile | dP^T half-tile}
+  // PSM (d = 32): THREE elementwise warpgroups, P^T through shared memory.  ncu / timelines of the 2-warpgroup kernel: no pipe above
+  // 45 %, issue slots 55 % busy, two elementwise warps per scheduler -- the stage is bound by the latency of its own dependent
+  // chains, and a score slot is held from the score GEMMs until the dV GEMM has consumed the P^T written over it (cycle
+  // X -> elementwise -> YV -> X of ~3800 clk per three units).  Here unit u is processed by warpgroup u % 3 out of slot u % 3;
+  // P^T goes to a ring of NPB boxes in shared memory ([kv][q] fp16, the layout of the dS^T boxes; dV becomes an SS GEMM), so the
+  // slot returns to the score issuer as soon as its values are in registers (scores_free), and a third warp per scheduler
+  // fills the latency gaps of the other two.  640 threads; register budgets 48 / 120 / 72 (pool 640 x 96).
+  // (Probed and rejected: fp16 accumulators for the score GEMMs are NOT packed in TMEM -- one value per 32-bit column -- so they save
+  // neither columns nor tcgen05.ld traffic; and the TMEM read port is not the limit: 840 B / clk / SM measured, ~60 needed.)
+  static constexpr bool PSM = kBwdPsmem && D == 32 && !PRING;
+  static constexpr int NEW = PSM ? 3 : 2;              // elementwise warpgroups
+  static constexpr int THREADS = 128 * (2 + NEW);      // issuers + elementwise + drain
+  static constexpr int NPB = 3;                        // PSM: P^T boxes, unit u -> u % NPB
+  static constexpr int SLOT_COLS = 128;                // {S^T half-tile | dP^T half-tile}
   static constexpr int HALF_COLS = SLOT_COLS / 2;
   static constexpr int NSLOT = PRING ? 2 : (D <= 32 ? 3 : (D == 64 ? 2 : 1));
   static constexpr int NPR = (D <= 32) ? 4 : 2;  // PRING: P^T buffers (unit u -> u % NPR)
@@ -136,7 +148,7 @@ struct BwdBars {
   uint64_t dq_empty[2], fin_full;
   // PRING: scores_free[h] (128 arrivals: warpgroup h has loaded the scores of its unit), p_free[u % NPR] (YV: dV of the unit has
   // consumed the P^T buffer)
-  uint64_t scores_free[2], p_free[4];
+  uint64_t scores_free[3], p_free[4];
   uint32_t tmem_base;
 };
 
@@ -209,7 +221,7 @@ __device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async
 // (r02 also tried FOUR elementwise warpgroups at 768 threads / 80 registers: better MUFU utilisation per unit, 76 % instead of
 // 60 %, but with one score slot the four groups run in lockstep and nothing overlaps the score GEMMs: 2.6 ms instead of 2.25.)
 template <int D, bool BF16>
-__global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1) attn_bwd_umma_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = BwdCfg<D>;
   constexpr int SW = Cfg::SW;
   constexpr int NST = Cfg::STAGES;
@@ -249,6 +261,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
   uint8_t* sDO = smem + Cfg::OFF_DO;
   uint8_t* sDST = smem + Cfg::OFF_DST;
   uint8_t* sDQS = smem + Cfg::OFF_DQS;
+  uint8_t* sPT = smem + Cfg::OFF_PT;   // PSM only
   BwdBars* bars = reinterpret_cast<BwdBars*>(smem + Cfg::OFF_BAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -267,7 +280,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     // conversion is on the critical path of every tile -- by the two elementwise warpgroups together (256 arrivals)
     for (int i = 0; i < 4; ++i) mbar_init(&bars->q_ready[i], NST == 1 ? 256 : 128);
     for (int i = 0; i < 3; ++i) mbar_init(&bars->slot_free[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&bars->scores_free[i], 128);
+    for (int i = 0; i < 3; ++i) mbar_init(&bars->scores_free[i], 128);
     for (int i = 0; i < 4; ++i) mbar_init(&bars->p_free[i], 1);
     fence_barrier_init();
   }
@@ -281,7 +294,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
   const float ds_scale = ds_scale_from_amax(__ldg(p.dout_amax_bits));  // 2^-e
 
   if (warp < 4) {
-    reg_dealloc<64>();
+    if constexpr (Cfg::PSM) reg_dealloc<48>(); else reg_dealloc<64>();
     // ---------------- MMA issuers ----------------
     // Work is pipelined in "units" u = 2 i + h: half h (64 query rows) of query tile i.  Unit u's scores live in TMEM
     // slot u % NSLOT; warpgroup h turns them into P^T (fp16, over the front of the slot) and the dS^T box (pair i & 1,
@@ -295,8 +308,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     const bool leader = lane == 0;
     const int U = 2 * T;
     if (warp == 0) {
-      // S^T, dP^T half-tiles (fp16 x fp16); ACC16: fp16 accumulators (c_format bits [4, 6) = 0)
-      constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, false, false) & (Cfg::ACC16 ? ~(3u << 4) : ~0u);
+      constexpr uint32_t idesc_s = make_idesc(128, 64, false, false, false, false);  // S^T, dP^T half-tiles (fp16 x fp16)
       const uint64_t dk_k = desc_kmajor<SW>(smem_u32(sK), 0);                        // K as K-major A (S^T)
       const uint64_t dv_k = desc_kmajor<SW>(smem_u32(sV), 0);                        // V as K-major A (dP^T)
       const uint64_t dq_k = desc_kmajor<SW>(smem_u32(sQ), 0);                        // Q_i rows as K-major B
@@ -309,6 +321,11 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         if (Cfg::PRING) {
           if (i >= 1) {  // warpgroup hf has loaded the scores of its previous unit out of this slot
             mbar_wait(&bars->scores_free[hf], (i - 1) & 1);
+            tc_fence_after_sync();
+          }
+        } else if (Cfg::PSM) {
+          if (u >= NSLOT) {  // warpgroup (u - NSLOT) % 3 has loaded the scores of unit u - NSLOT out of this slot
+            mbar_wait(&bars->scores_free[slot], (u / NSLOT - 1) & 1);
             tc_fence_after_sync();
           }
         } else if (u >= NSLOT) {  // the slot still holds P^T of unit u - NSLOT until its dV GEMM has completed
@@ -357,11 +374,21 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         const uint32_t tp = Cfg::PRING ? tmem + Cfg::TMEM_P + (u % Cfg::NPR) * 32 : tmem + Cfg::TMEM_SLOT + slot * Cfg::SLOT_COLS;
         if (leader) {
           HSTU_TSTAMP(1, u, 1);
+          if constexpr (Cfg::PSM) {
+            // A = the unit's P^T box in shared memory (K-major, like the dS^T box of the dK GEMM)
+            const uint64_t dpt_k = desc_kmajor<128>(smem_u32(sPT), 0) + (uint64_t)(((u % Cfg::NPB) * 16384) >> 4);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_ss(tmem + Cfg::TMEM_DV, dpt_k + (uint64_t)((ks * 32) >> 4), ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv,
+                     (u > 0) || (ks > 0));
+            mma_commit(&bars->p_free[u % Cfg::NPB]);   // the P^T box may be rewritten
+          } else {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)  // K = the 64 query rows of this half
             mma_ts(tmem + Cfg::TMEM_DV, tp + ks * 8, ddo_mn + rows + (uint64_t)((ks * 16 * SW) >> 4), idesc_kv, (u > 0) || (ks > 0));
           // PRING: the P^T buffer may be rewritten; otherwise: the score issuer may overwrite the slot
           mma_commit(Cfg::PRING ? &bars->p_free[u % Cfg::NPR] : &bars->slot_free[slot]);
+          }
           if (hf == 1) mma_commit(&bars->tile_done[i & 3]);  // this issuer is done with dO_i
           HSTU_TSTAMP(1, u, 2);
         }
@@ -420,8 +447,8 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         __syncwarp();
       }
     }
-  } else if (warp >= 12) {
-    reg_dealloc<96>();
+  } else if (warp >= 4 + 4 * Cfg::NEW) {
+    if constexpr (Cfg::PSM) reg_dealloc<72>(); else reg_dealloc<96>();
     // ---------------- dQ drain warpgroup (+ TMA producer on its elected lane) ----------------
     // dQ tile of query tile i: TMEM (lane = query row) -> swizzled fp32 staging box (32 columns) in shared memory -> ONE TMA
     // reduce-add per box into dq_acc.  Two staging boxes alternate, so a reduce may still be reading one while the next is being
@@ -431,7 +458,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     const int quad = warp & 3;
     const int row = quad * 32 + lane;              // query row inside the tile == TMEM lane
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
-    const bool elected = warp == 12 && lane == 0;
+    const bool elected = warp == 4 + 4 * Cfg::NEW && lane == 0;
     auto load_tile = [&](int i) {
       const int st = i % NST;
       mbar_arrive_expect_tx(&bars->q_full[st], 2 * Cfg::TILE_BYTES);
@@ -456,7 +483,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
       }
       for (int i = 0; i < NST && i < T; ++i) load_tile(i);
     }
-    const int ct = tid - 384;  // index inside this warpgroup
+    const int ct = tid - 128 * (1 + Cfg::NEW);  // index inside this warpgroup
     auto convert_tile = [&](int i) {  // Q_i (as is) and dO_i (times 2^-e) of stage i % NST: bf16 -> fp16 in place
       const int st = i % NST;
       mbar_wait(&bars->q_full[st], (i / NST) & 1);
@@ -488,6 +515,23 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         const uint32_t sbox = smem_u32(sDQS + (box & 1) * Cfg::DQS_BYTES);
         if (elected) bulk_wait_group_read1();      // the reduce that used this box (two boxes ago) has finished reading it
         named_bar_sync(1, 128);
+        if constexpr (Cfg::PSM) {
+          // 72 registers in this mode: two loads of 16 columns instead of one of 32 (which spilled 22 registers per tile)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t r[16];
+            tmem_ld16(tmem + Cfg::TMEM_DQ + (i % Cfg::NDQ) * D + ps * 32 + hh * 16 + lane_bits, r);
+            tmem_ld_wait();
+            if (hh == 1 && ps == Cfg::DQ_NPASS - 1) {
+              tc_fence_before_sync();
+              mbar_arrive(&bars->dq_empty[i % Cfg::NDQ]);
+            }
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              st_shared_v4(sbox + swizzled_chunk_offset<128>(row, hh * 4 + (e >> 2)), q_ok ? r[e] : 0u, q_ok ? r[e + 1] : 0u,
+                           q_ok ? r[e + 2] : 0u, q_ok ? r[e + 3] : 0u);
+          }
+        } else {
         uint32_t r[32];
         tmem_ld32(tmem + Cfg::TMEM_DQ + (i % Cfg::NDQ) * D + ps * 32 + lane_bits, r);
         tmem_ld_wait();
@@ -499,6 +543,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         for (int e = 0; e < 32; e += 4)
           st_shared_v4(sbox + swizzled_chunk_offset<128>(row, e >> 2), q_ok ? r[e] : 0u, q_ok ? r[e + 1] : 0u,
                        q_ok ? r[e + 2] : 0u, q_ok ? r[e + 3] : 0u);
+        }
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (elected) {
@@ -519,7 +564,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     }
     if (elected) bulk_wait_group_read0();          // shared memory must stay valid until the last reduce has read it
   } else {
-    reg_alloc<176>();
+    if constexpr (Cfg::PSM) reg_alloc<120>(); else reg_alloc<176>();
     // ---------------- elementwise warpgroups ----------------
     const int wg = (warp - 4) >> 2;                // owns query columns [64*wg, 64*wg + 64) of every tile
     const int quad = warp & 3;
@@ -595,6 +640,55 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     }                                                                                                          \
   }
 
+    if constexpr (Cfg::PSM) {
+      // warpgroup wg takes units wg, wg + 3, ...: unit u = 2 i + hf lives in slot u % 3 == wg
+      for (int u = wg; u < 2 * T; u += 3) {
+        const int i = u >> 1, hf = u & 1, slot = wg;
+        const int m0 = q_tile(i) * 128;
+        const int cbase = hf * 64;                    // query columns [64 hf, 64 hf + 64) of the tile
+        if (stamp) HSTU_TSTAMP(wg == 2 ? 7 : 2 + wg, u, 0);
+        mbar_wait(&bars->s_full[slot], (u / 3) & 1);
+        tc_fence_after_sync();
+        if (stamp) HSTU_TSTAMP(wg == 2 ? 7 : 2 + wg, u, 1);
+        const int mh0 = m0 + cbase;
+        const bool full = fast && (mh0 >= n0 + 128) && (mh0 + 64 <= len) && (!msk.has_tgt || n0 + 128 <= msk.max_id);
+        const int mode = full ? 0 : (fast ? 1 : 2);
+        const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + hf * 16384);
+        const uint32_t sPTw = smem_u32(sPT + (u % Cfg::NPB) * 16384);
+        const int jr = j_pos - m0 - cbase;
+        const int len_rel = len - m0 - cbase;
+        const uint32_t st_addr = tmem + Cfg::TMEM_SLOT + slot * Cfg::SLOT_COLS + lane_bits;
+        const uint32_t dp_addr = st_addr + Cfg::HALF_COLS;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t s[32], dp[32];
+          tmem_ld32(st_addr + c * 32, s);
+          tmem_ld32(dp_addr + c * 32, dp);
+          tmem_ld_wait();
+          if (c == 1) {
+            tc_fence_before_sync();
+            mbar_arrive(&bars->scores_free[slot]);     // both chunks are in registers: the slot goes back to the score issuer
+          } else {
+            if (i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);   // GEMMs of tile i-2 are done with the dS^T box pair
+            if (u >= Cfg::NPB) mbar_wait(&bars->p_free[u % Cfg::NPB], ((u / Cfg::NPB) - 1) & 1);  // dV of unit u - NPB has read this P^T box
+          }
+          uint32_t pp[16], dd[16];
+#define HSTU_S32(e) s[e]
+#define HSTU_D32(e) dp[e]
+          HSTU_BWD_RUN(32, HSTU_S32, HSTU_D32, pp, dd, c * 32);
+#undef HSTU_S32
+#undef HSTU_D32
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            st_shared_v4(sPTw + swizzled_chunk_offset<128>(row, c * 4 + j4), pp[4 * j4], pp[4 * j4 + 1], pp[4 * j4 + 2], pp[4 * j4 + 3]);
+            st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + j4), dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        if (stamp) HSTU_TSTAMP(wg == 2 ? 7 : 2 + wg, u, 2);
+        mbar_arrive(&bars->unit_done[hf * 2 + (i & 1)]);
+      }
+    } else
     for (int i = 0; i < T; ++i) {
       const int u = 2 * i + wg, slot = u % Cfg::NSLOT;
       const int m0 = q_tile(i) * 128;
@@ -694,26 +788,9 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
 #pragma unroll
         for (int c = 0; c < 2; ++c) {  // 2 chunks of 32 query columns
           uint32_t s[32], dp[32];
-          if constexpr (Cfg::ACC16) {
-            // fp16 accumulators: 32 values = 16 columns of packed pairs; widened to fp32 here (the arithmetic stays fp32)
-            uint32_t s16[16], dp16[16];
-            tmem_ld16(st_addr + c * 16, s16);
-            tmem_ld16(dp_addr + c * 16, dp16);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float2 sf = __half22float2(*reinterpret_cast<const __half2*>(&s16[e]));
-              const float2 df = __half22float2(*reinterpret_cast<const __half2*>(&dp16[e]));
-              s[2 * e] = __float_as_uint(sf.x);
-              s[2 * e + 1] = __float_as_uint(sf.y);
-              dp[2 * e] = __float_as_uint(df.x);
-              dp[2 * e + 1] = __float_as_uint(df.y);
-            }
-          } else {
-            tmem_ld32(st_addr + c * 32, s);
-            tmem_ld32(dp_addr + c * 32, dp);
-            tmem_ld_wait();
-          }
+          tmem_ld32(st_addr + c * 32, s);
+          tmem_ld32(dp_addr + c * 32, dp);
+          tmem_ld_wait();
           if (c == 0 && i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // GEMMs of tile i-2 are done with this box pair
           uint32_t pp[16], dd[16];
 #define HSTU_S32(e) s[e]
@@ -740,6 +817,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
     mbar_wait(&bars->fin_full, 0);
     tc_fence_after_sync();
     const bool is_dv = wg == 0;
+    if (wg < 2) {
     const int ecol0 = 0;
     const uint32_t acc = tmem + (is_dv ? Cfg::TMEM_DV : Cfg::TMEM_DK) + ecol0 + lane_bits;
     // undo 2^-e (a power of two: exact): dK always carries it, dV only when dO itself was scaled
@@ -763,6 +841,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_umma_kernel(const __grid_cons
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
+    }
     }
   }
   tc_fence_before_sync();
@@ -874,21 +953,21 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   dim3 grid((p.max_seq_len + 127) / 128, p.heads, p.batch);
 #ifdef HSTU_TRACE
   long long* tbuf = nullptr;
-  const size_t tbytes = sizeof(long long) * 7 * 256 * 4;
+  const size_t tbytes = sizeof(long long) * 8 * 256 * 4;
   cudaMalloc(&tbuf, tbytes);
   cudaMemset(tbuf, 0, tbytes);
   cudaMemcpyToSymbol(g_trace, &tbuf, sizeof(tbuf));
 #endif
-  kern<<<grid, 512, Cfg::SMEM_BYTES, st>>>(bp);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(bp);
   HSTU_CUDA_OK(cudaGetLastError());
 #ifdef HSTU_TRACE
   {
     cudaDeviceSynchronize();
-    static long long host[7 * 256 * 4];
+    static long long host[8 * 256 * 4];
     cudaMemcpy(host, tbuf, tbytes, cudaMemcpyDeviceToHost);
     FILE* f = fopen("gpurun_out/bwd_trace.txt", "w");
     if (f) {
-      for (int r = 0; r < 7; ++r)
+      for (int r = 0; r < 8; ++r)
         for (int i = 0; i < 256; ++i) {
           const long long* e = host + (r * 256 + i) * 4;
           if (e[0] || e[1] || e[2] || e[3]) fprintf(f, "%d %d %lld %lld %lld %lld\n", r, i, e[0], e[1], e[2], e[3]);

@@ -122,6 +122,94 @@ def run_pring(T, d, seed):
     return _simulate(actors, B, rnd)
 
 
+def run_psm(T, seed, NST=4, NPB=3, NDQ=2):
+    """PSM mode (d = 32, -DHSTU_BWD_PSMEM): three elementwise warpgroups (unit u -> warpgroup u % 3 -> score slot u % 3), the slot is
+    handed back right after the load (scores_free), P^T goes to a ring of NPB shared-memory boxes released by the dV commits."""
+    rnd = random.Random(seed)
+    B = {"kv": Bar(1), "kvr": Bar(1), "fin": Bar(2)}
+    for i in range(4):
+        B[f"qf{i}"], B[f"qr{i}"], B[f"td{i}"], B[f"ud{i}"], B[f"pf{i}"] = Bar(1), Bar(1), Bar(3), Bar(1), Bar(1)
+    for i in range(3):
+        B[f"sf{i}"], B[f"free{i}"] = Bar(1), Bar(1)
+    for i in range(2):
+        B[f"dqe{i}"] = Bar(1)
+    U = 2 * T
+
+    def ud(u):
+        i, hf = u >> 1, u & 1
+        return f"ud{hf * 2 + (i & 1)}", i >> 1
+
+    def X():
+        yield ("wait", "kvr", 0)
+        for u in range(U):
+            i, hf = u >> 1, u & 1
+            if u >= 3:
+                yield ("wait", f"free{u % 3}", u // 3 - 1)
+            if hf == 0:
+                yield ("wait", f"qr{i % NST}", i // NST)
+            yield ("async", f"sf{u % 3}")
+
+    def YV():
+        for u in range(U):
+            i, hf = u >> 1, u & 1
+            yield ("wait",) + ud(u)
+            yield ("async", f"pf{u % NPB}")
+            if hf == 1:
+                yield ("async", f"td{i & 3}")
+        yield ("async", "fin")
+
+    def YK():
+        for u in range(U):
+            i, hf = u >> 1, u & 1
+            yield ("wait",) + ud(u)
+            if hf == 1:
+                yield ("async", f"td{i & 3}")
+        yield ("async", "fin")
+
+    def Z():
+        yield ("wait", "kvr", 0)
+        for i in range(T):
+            yield ("wait",) + ud(2 * i)
+            yield ("wait",) + ud(2 * i + 1)
+            if i >= NDQ:
+                yield ("wait", f"dqe{i % NDQ}", i // NDQ - 1)
+            yield ("async", f"td{i & 3}")
+
+    def W(w):
+        for u in range(w, U, 3):
+            i = u >> 1
+            yield ("wait", f"sf{w}", u // 3)
+            if i >= 2:
+                yield ("wait", f"td{(i - 2) & 3}", (i - 2) >> 2)
+            if u >= NPB:
+                yield ("wait", f"pf{u % NPB}", u // NPB - 1)
+            yield ("arrive", f"free{w}")     # second chunk loaded: the slot goes back to the issuer
+            yield ("arrive", ud(u)[0])
+        yield ("wait", "fin", 0)
+
+    def Dr():
+        yield ("async", "kv")
+        for i in range(min(NST, T)):
+            yield ("async", f"qf{i % NST}")
+        yield ("wait", "kv", 0)
+        yield ("arrive", "kvr")
+        for i in range(min(NST, T)):
+            yield ("wait", f"qf{i % NST}", i // NST)
+            yield ("arrive", f"qr{i % NST}")
+        for i in range(T):
+            yield ("wait", f"td{i & 3}", i >> 2)
+            if i + NST < T:
+                yield ("async", f"qf{(i + NST) % NST}")
+            yield ("arrive", f"dqe{i % NDQ}")
+            t = i - 1 + NST
+            if i >= 1 and t < T:
+                yield ("wait", f"qf{t % NST}", t // NST)
+                yield ("arrive", f"qr{t % NST}")
+
+    actors = {"X": X(), "YV": YV(), "YK": YK(), "Z": Z(), "W0": W(0), "W1": W(1), "W2": W(2), "D": Dr()}
+    return _simulate(actors, B, rnd)
+
+
 def _simulate(actors, B, rnd):
     pending = {k: None for k in actors}
     queues = {k: [] for k in actors}

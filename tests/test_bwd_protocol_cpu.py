@@ -25,6 +25,13 @@ def test_pring_variant_protocol(d):
             sim.run_variant_pring(tiles, d, seed)
 
 
+def test_psm_mode_protocol():
+    """d = 32 with three elementwise warpgroups and the P^T boxes in shared memory (-DHSTU_BWD_PSMEM)."""
+    for tiles in (1, 2, 3, 4, 5, 7, 8, 13, 64):
+        for seed in range(25):
+            sim.run_psm(tiles, seed)
+
+
 def test_model_reproduces_the_two_bugs_found_on_the_gpu():
     # one s_full barrier with a single score slot: warpgroup 1 asks for phase 1 before phase 0 completed
     with pytest.raises(sim.Violation, match="false pass"):
