@@ -527,7 +527,7 @@ __global__ void silu_kernel(const T* __restrict__ x, const T* __restrict__ dy, T
                             int n_cols, long long xs, long long dys, long long os) {
   // U independent 16-byte vectors per thread and iteration: all loads are issued before the first use, so that a thread has
   // U (forward) or 2 U (backward) requests in flight -- with one, 64 resident warps cover only half of the bandwidth-delay product
-  constexpr int U = VEC == 1 ? 1 : (BWD ? 2 : 4);
+  constexpr int U = (VEC == 1 || BWD) ? 1 : 4;  // measured: the backward (two input streams) is fastest with one vector per thread
   const int vec_per_row = n_cols / VEC;
   const long long total = n_rows * vec_per_row;
   // a CTA works on contiguous chunks of U * blockDim vectors (thread t: vectors t, t + blockDim, ...): the U requests of a thread
@@ -826,9 +826,10 @@ static int silu_t(const void* x, const void* dy, void* out, long long n, int col
   constexpr int VEC = 16 / sizeof(T);
   const bool v = can_vec<T>(cols, {x, dy, out}, {xs, dys, os});
   const long long total = n * (cols / (v ? VEC : 1));
-  const int per_thread = v ? (bwd ? 2 : 4) : 1;  // the kernel's U
+  const int per_thread = (v && !bwd) ? 4 : 1;  // the kernel's U
   long long blocks = (total + 256 * per_thread - 1) / (256 * per_thread);
-  if (blocks > 148 * 8) blocks = 148 * 8;  // one resident wave
+  const long long cap = bwd ? 148 * 16 : 148 * 8;
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
 #define LAUNCH(VV, BB) silu_kernel<T, VV, BB><<<(int)blocks, 256, 0, st>>>((const T*)x, (const T*)dy, (T*)out, n, cols, xs, dys, os)
   if (bwd) {

@@ -9,3 +9,4 @@ for v in default "$@"; do
   r=$(timeout 300 python bench.py --workload attn --batch 16 --attn-heads 8 --attn-dim 32 --lmax 8192 --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print('fwd %.3f bwd %.3f'%(r['fwd']['ms_per_launch'], r['ms_per_launch']))")
   echo "[$v] d=32: $r" | tee -a gpurun_out/ab.txt
 done
+unset HSTU_B200_LIB; echo "[rowwise] $(timeout 300 python scripts/rowwise_bench.py 2>&1 | tail -1)" | tee gpurun_out/rowwise_fast.txt
