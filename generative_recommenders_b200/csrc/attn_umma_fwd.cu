@@ -83,9 +83,20 @@ struct FwdBars {
   uint32_t tmem_base;
 };
 
+// THREE silu warpgroups for d <= 64 (tile i -> warpgroup i % 3 == its score slot), two otherwise: at d <= 64 the kernel is bound by
+// the MUFU pipe (one tanh per score; ncu: 70 % busy with two warpgroups) and each warpgroup leaves it idle while it waits for
+// its next scores, loads and stores; a third warp per scheduler fills those gaps.
+#ifdef HSTU_FWD_3WG
+template <int D> constexpr int kFwdSiluWgs = (D <= 64) ? 3 : 2;
+#else
+template <int D> constexpr int kFwdSiluWgs = 2;
+#endif
+template <int D, bool BF16> constexpr int kFwdThreads = 128 * (1 + kFwdSiluWgs<D> + (BF16 ? 1 : 0));
+
 template <int D, bool BF16>
-__global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(const __grid_constant__ FwdParams p) {
   using Cfg = FwdCfg<D>;
+  constexpr int NWG = kFwdSiluWgs<D>;
   constexpr bool CONV = BF16;  // bf16 V tiles are converted to fp16 in shared memory: P.V runs fp16 x fp16
   constexpr int SW = Cfg::SW;
   constexpr int NST = Cfg::STAGES;
@@ -138,10 +149,10 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
   uint64_t* const v_rdy = CONV ? bars->v_ready : bars->v_full;
   // bf16 inputs run 512 threads (128 registers / thread at launch): per-warpgroup budgets are set at the top of each role
 
-  if (warp >= 12) {
+  if (warp >= 4 + 4 * NWG) {
     // ---------------- converter warpgroup (bf16 inputs): TMA-landed tile -> fp16 in place -> ready ----------------
-    reg_dealloc<64>();
-    const int t = tid - 384;
+    if constexpr (NWG == 3) reg_dealloc<56>(); else reg_dealloc<64>();
+    const int t = tid - 128 * (1 + NWG);
     for (int i = 0; i < T; ++i) {
       const int st = i % NST;
       mbar_wait(&bars->v_full[st], (i / NST) & 1);
@@ -150,7 +161,7 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
       mbar_arrive(&bars->v_ready[st]);
     }
   } else if (warp < 4) {
-   if (CONV) reg_dealloc<80>();
+   if (CONV) { if constexpr (NWG == 3) reg_dealloc<56>(); else reg_dealloc<80>(); }
    if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer: Q, then K tiles ----------------
@@ -252,7 +263,7 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
    }
   } else {
     // ---------------- silu warpgroups ----------------
-    if (CONV) reg_alloc<168>();
+    if (CONV) { if constexpr (NWG == 3) reg_alloc<120>(); else reg_alloc<168>(); }
     const int wg = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;              // query row inside the tile == TMEM lane
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
     // plain causal (+targets): valid(i, j) = (j < lim_i) | (j == i)   (common.cuh: mask_valid, fast path)
     const int lim_i = msk.has_tgt ? min(i_pos, msk.max_id) : i_pos;
     const int full_lim = fast ? min(m0, msk.has_tgt ? msk.max_id : 0x7fffffff) : -1;
-    for (int i = wg, it = 0; i < T; i += 2, ++it) {
+    for (int i = wg, it = 0; i < T; i += NWG, ++it) {
       const uint32_t s_taddr = tmem + Cfg::TMEM_S + (i % NSL) * 128 + lane_bits;
       mbar_wait(&bars->s_full[i % NSL], (i / NSL) & 1);
       tc_fence_after_sync();
@@ -328,7 +339,8 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
     mbar_wait(&bars->o_full, 0);
     tc_fence_after_sync();
     constexpr int HALF = D / 2;
-    const int cbase = wg * HALF;
+    const int cbase = (wg & 1) * HALF;
+    if (wg < 2) {
     uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + (row0 + m0 + row) * p.o_row_stride + (long long)h * p.o_head_stride + cbase;
 #pragma unroll
     for (int c = 0; c < HALF / 16; ++c) {
@@ -354,6 +366,7 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_kernel(cons
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
+    }
     }
   }
   tc_fence_before_sync();
@@ -413,7 +426,7 @@ static int launch_fwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   auto kern = attn_fwd_umma_kernel<D, BF16>;
   HSTU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   dim3 grid((p.max_seq_len + 127) / 128, p.heads, p.batch);
-  kern<<<grid, BF16 ? 512 : 384, Cfg::SMEM_BYTES, st>>>(fp);
+  kern<<<grid, kFwdThreads<D, BF16>, Cfg::SMEM_BYTES, st>>>(fp);
   HSTU_CUDA_OK(cudaGetLastError());
   return 0;
 }
