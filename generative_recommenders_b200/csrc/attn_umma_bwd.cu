@@ -513,6 +513,13 @@ __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1) attn_bwd_umma_kernel(co
 #pragma unroll
       for (int ps = 0; ps < Cfg::DQ_NPASS; ++ps, ++box) {
         const uint32_t sbox = smem_u32(sDQS + (box & 1) * Cfg::DQS_BYTES);
+#ifdef HSTU_EXP_BWD_NO_DRAIN
+        if (ps == Cfg::DQ_NPASS - 1) {  // ablation (wrong numerics): no dQ traffic at all
+          tc_fence_before_sync();
+          mbar_arrive(&bars->dq_empty[i % Cfg::NDQ]);
+        }
+        continue;
+#endif
         if (elected) bulk_wait_group_read1();      // the reduce that used this box (two boxes ago) has finished reading it
         named_bar_sync(1, 128);
         if constexpr (Cfg::PSM) {
@@ -785,6 +792,10 @@ __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1) attn_bwd_umma_kernel(co
             st_shared_v4(sDSTw + swizzled_chunk_offset<128>(row, c * 4 + j4), dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
         }
       } else {
+#ifdef HSTU_EXP_BWD_NO_ELEM
+        if (i >= 2) mbar_wait(&bars->tile_done[(i - 2) & 3], ((i - 2) >> 2) & 1);  // ablation (wrong numerics): barriers only
+        if (T < 0)
+#endif
 #pragma unroll
         for (int c = 0; c < 2; ++c) {  // 2 chunks of 32 query columns
           uint32_t s[32], dp[32];
