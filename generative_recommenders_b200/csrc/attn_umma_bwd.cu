@@ -51,13 +51,6 @@ struct alignas(64) BwdParams {
   float alpha_half;
   float dv_scale;  // 1 / N
   float dk_scale;  // alpha / N
-  // relative attention bias of the research block (hstu.py:124-143) and its fp32 gradient accumulators; all NULL without it
-  const float* pos_w;           // [2 n - 1]
-  const float* ts_w;            // [num_ts_buckets + 1]
-  const long long* timestamps;  // [B, n]
-  float* dpos_w;
-  float* dts_w;
-  int num_ts_buckets;
 };
 
 #ifdef HSTU_BWD_PSMEM
@@ -89,15 +82,8 @@ struct BwdCfg {
   static constexpr int OFF_DQS = OFF_DST + 2 * PT_BYTES;
   static constexpr int OFF_PT = OFF_DQS + 2 * DQS_BYTES;   // PSM: NPB P^T boxes [128 kv][64 q] fp16
   static constexpr int OFF_BAR = OFF_PT + ((kBwdPsmem && D == 32) ? 3 * 16384 : 0);
-  // relative-bias gradients (d = 32): per elementwise warpgroup a window of the 191 diagonals of its half-tile (position bias),
-  // one histogram of up to 1024 time buckets for the CTA
-  static constexpr bool BIAS_OK = (D == 32);
-  static constexpr int HIST_POS = 192, HIST_TS = 1024;
-  static constexpr int BAR_BYTES = 512;             // sizeof(BwdBars) <= 512 is asserted next to the struct
-  static constexpr int OFF_HIST = OFF_BAR + BAR_BYTES;
-  static constexpr int HIST_BYTES = BIAS_OK ? (2 * HIST_POS + HIST_TS) * 4 : 0;
-  static_assert(OFF_HIST + HIST_BYTES + 1024 <= 232448, "shared memory budget");
-  static constexpr int SMEM_BYTES = OFF_HIST + HIST_BYTES + 1024;
+  static_assert(OFF_BAR + 256 + 1024 <= 232448, "shared memory budget");
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   // TMEM: a ring of NSLOT score slots, each {S^T half-tile: 64 columns, dP^T half-tile: 64 columns} (a half-tile is
   // 128 key rows x 64 query rows; after the elementwise stage the front of the S^T half holds P^T as bf16), the dV and
   // dK accumulators and NDQ dQ accumulators (tile i -> buffer i % NDQ; with two, the warpgroups drain dQ two tiles late and
@@ -165,7 +151,6 @@ struct BwdBars {
   uint64_t scores_free[3], p_free[4];
   uint32_t tmem_base;
 };
-static_assert(sizeof(BwdBars) <= 512, "BwdBars must fit the bytes reserved for it (BwdCfg::BAR_BYTES)");
 
 #ifdef HSTU_TRACE
 // Debug timeline: CTA (0,0,0) records clock64() stamps of its pipeline events into g_trace[role][index][slot].
@@ -606,21 +591,6 @@ __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1) attn_bwd_umma_kernel(co
     const bool j_hist = j_ok && (!msk.has_tgt || j_pos < msk.max_id);  // fast mask: valid = (j_hist & i > j) | (i == j)
     const int cbase = wg * 64;
     const bool stamp = quad == 0 && lane == 0;
-    // relative bias (ring path, d = 32): tables, this thread's key timestamp, gradient histograms in shared memory
-    constexpr bool BIAS_PATH = Cfg::BIAS_OK && !Cfg::PRING && !Cfg::PSM;
-    const bool has_bias = BIAS_PATH && (p.pos_w != nullptr || p.ts_w != nullptr);
-    const int nmax = p.max_seq_len;
-    const int j_cl = min(j_pos, nmax - 1);
-    const long long* ts_row = p.timestamps ? p.timestamps + (long long)b * nmax : nullptr;
-    const long long ts_j = (has_bias && p.ts_w) ? __ldg(ts_row + j_cl) : 0;
-    float* hist = reinterpret_cast<float*>(smem + Cfg::OFF_HIST);
-    float* hpos = hist + wg * Cfg::HIST_POS;          // this warpgroup's window of diagonals
-    float* hts = hist + 2 * Cfg::HIST_POS;            // shared by both warpgroups
-    const float hist_scale = 0.5f * p.dv_scale / ds_scale;   // dS^T holds 2 * 2^-e * N * dS
-    if (has_bias) {
-      for (int t = tid - 128; t < 2 * Cfg::HIST_POS + Cfg::HIST_TS; t += 256) hist[t] = 0.f;
-      named_bar_sync(4, 256);
-    }
 
     // p = x sig(x) and 2 dS = dP (1 + g2) from one tanh; packed fp32x2 arithmetic (FMUL2 / FFMA2): two elements per issued
     // instruction, one MUFU.TANH per element
@@ -636,63 +606,12 @@ __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1) attn_bwd_umma_kernel(co
     const float2 dv = __ffma2_rn(dpe, g2, dpe);                 /* 2 dS = dP (1 + g2)                  */      \
     P0 = pv.x; P1 = pv.y; D0 = dv.x; D1 = dv.y;                                                                \
   }
-    // Relative bias (research block, d = 32 only; hstu.py:124-143): x = alpha s + pos_w[n - 1 + j - i] + ts_w[bucket(ts[i + 1] - ts[j])].
-    // Scalar code, tables read through L1; the gradients of the two tables are the sums of dS over all scores that used an entry:
-    // position bias -> the 191 diagonals of this half-tile in shared memory (lanes hold consecutive key rows: no conflicts),
-    // time bias -> one shared histogram, lanes of a warp mostly agree on the bucket so the warp sums first.  Both carry the factor
-    // 2 * 2^-e / ... of dS^T and are scaled when they are flushed.
-#define HSTU_BWD_MODE3_BODY(NE, SREF, DREF, PP, DD, col0)                                                      \
-  _Pragma("unroll") for (int e = 0; e < NE; e += 2) {                                                          \
-    float pq2[2], dq2[2];                                                                                      \
-    _Pragma("unroll") for (int q = 0; q < 2; ++q) {                                                            \
-      const int il = (col0) + e + q;                                                                           \
-      const int i_pos = m0 + cbase + il;                                                                       \
-      const int ic = min(i_pos, nmax - 1);                                                                     \
-      float bias = 0.f;                                                                                        \
-      int bk = -1;                                                                                             \
-      if (p.pos_w) bias += __ldg(p.pos_w + (nmax - 1 + j_cl - ic));                                            \
-      if (p.ts_w) {                                                                                            \
-        bk = ts_bucket(__ldg(ts_row + min(ic + 1, nmax - 1)) - ts_j, p.num_ts_buckets);                        \
-        bias += __ldg(p.ts_w + bk);                                                                            \
-      }                                                                                                        \
-      const float hh = fmaf(__uint_as_float(SREF(e + q)), p.alpha_half, 0.5f * bias);                          \
-      const float t = tanh_approx(hh);                                                                         \
-      float pv = fmaf(hh, t, hh);                                                                              \
-      const float g2 = fmaf(hh, fmaf(-t, t, 1.f), t);                                                          \
-      float dpe = __uint_as_float(DREF(e + q));                                                                \
-      if (!CONV) dpe *= ds_scale;                                                                              \
-      float dv = fmaf(dpe, g2, dpe);                                                                           \
-      const bool ok = j_ok && i_pos < len && mask_valid(msk, i_pos, j_pos);                                    \
-      pv = ok ? pv : 0.f;                                                                                      \
-      dv = ok ? dv : 0.f;                                                                                      \
-      pq2[q] = pv;                                                                                             \
-      dq2[q] = dv;                                                                                             \
-      if (p.dpos_w && dv != 0.f) atomicAdd(hpos + (row - il + 63), dv);                                        \
-      if (p.dts_w) {                                                                                           \
-        const int key = ok ? bk : -1;                                                                          \
-        int same;                                                                                              \
-        __match_all_sync(0xffffffffu, key, &same);                                                             \
-        if (same) {                                                                                            \
-          float tsum = dv;                                                                                     \
-          _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);    \
-          if (lane == 0 && key >= 0 && tsum != 0.f) atomicAdd(hts + key, tsum);                                \
-        } else if (key >= 0 && dv != 0.f) {                                                                    \
-          atomicAdd(hts + key, dv);                                                                            \
-        }                                                                                                      \
-      }                                                                                                        \
-    }                                                                                                          \
-    PP[e >> 1] = pack_f16x2_sat(pq2[0], pq2[1]);                                                               \
-    DD[e >> 1] = pack_f16x2_sat(dq2[0], dq2[1]);                                                               \
-  }
-#define HSTU_BWD_MODE3(NE, SREF, DREF, PP, DD, col0)
     // NE consecutive query columns starting at column `col0` of this half: scores / dP (SREF(e), DREF(e) = element e of the run)
     // -> packed fp16 P^T (PP[e / 2]) and dS^T (DD[e / 2]).  ONE block of straight-line code per mask mode: the tile-uniform branch
     // sits outside, so the scheduler can interleave all NE / 2 independent MUFU -> FFMA2 chains (r02: with the branch and the
     // stores inside 16-column chunks every chunk exposed its own latency: 2750 clk per tile instead of 1700).
 #define HSTU_BWD_RUN(NE, SREF, DREF, PP, DD, col0)                                                             \
-  if (mode == 3) {                                                                                             \
-    HSTU_BWD_MODE3(NE, SREF, DREF, PP, DD, col0)                                                               \
-  } else if (mode == 0) {                                                                                             \
+  if (mode == 0) {                                                                                             \
     _Pragma("unroll") for (int e = 0; e < NE; e += 2) {                                                        \
       float p0, p1, d0, d1;                                                                                    \
       HSTU_BWD_ELEM2(SREF(e), SREF(e + 1), DREF(e), DREF(e + 1), p0, p1, d0, d1);                              \
@@ -796,7 +715,7 @@ __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1) attn_bwd_umma_kernel(co
       // classification of this half-tile (uniform over the warpgroup)
       const int mh0 = m0 + cbase;                   // first query row of the half
       const bool full = fast && (mh0 >= n0 + 128) && (mh0 + 64 <= len) && (!msk.has_tgt || n0 + 128 <= msk.max_id);
-      const int mode = has_bias ? 3 : (full ? 0 : (fast ? 1 : 2));
+      const int mode = full ? 0 : (fast ? 1 : 2);
       const uint32_t sDSTw = smem_u32(sDST + (i & 1) * Cfg::PT_BYTES + wg * 16384);
       const int jr = j_pos - m0 - cbase;           // query column (relative to this warpgroup's half) equal to j
       const int len_rel = len - m0 - cbase;        // columns >= len_rel are past the sequence end
@@ -887,12 +806,7 @@ __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1) attn_bwd_umma_kernel(co
           uint32_t pp[16], dd[16];
 #define HSTU_S32(e) s[e]
 #define HSTU_D32(e) dp[e]
-#undef HSTU_BWD_MODE3
-#define HSTU_BWD_MODE3(NE, SREF, DREF, PP, DD, col0) \
-  if constexpr (BIAS_PATH) { HSTU_BWD_MODE3_BODY(NE, SREF, DREF, PP, DD, col0) }
           HSTU_BWD_RUN(32, HSTU_S32, HSTU_D32, pp, dd, c * 32);
-#undef HSTU_BWD_MODE3
-#define HSTU_BWD_MODE3(NE, SREF, DREF, PP, DD, col0)
 #undef HSTU_S32
 #undef HSTU_D32
           // P^T chunk c (32 fp16 = 16 columns) overwrites the already-read front of the S^T half of the slot: A of the dV GEMM
@@ -907,29 +821,8 @@ __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1) attn_bwd_umma_kernel(co
       fence_proxy_async_smem();
       if (stamp) HSTU_TSTAMP(2 + wg, i, 2);
       mbar_arrive(&bars->unit_done[wg * 2 + (i & 1)]);
-      if (has_bias && p.dpos_w) {
-        // position-bias gradient of this half-tile: diagonal t - 63 = (key row) - (query column) -> pos_w index n - 1 + j - i
-        named_bar_sync(2 + wg, 128);
-        for (int t = tid - 128 - wg * 128; t < 191; t += 128) {
-          const float v = hpos[t];
-          if (v != 0.f) {
-            atomicAdd(p.dpos_w + (nmax - 1 + (n0 - m0 - cbase) + t - 63), v * hist_scale);
-            hpos[t] = 0.f;
-          }
-        }
-        named_bar_sync(2 + wg, 128);
-      }
-    }
-    if (has_bias && p.dts_w) {
-      named_bar_sync(4, 256);
-      for (int t = tid - 128; t <= p.num_ts_buckets; t += 256) {
-        const float v = hts[t];
-        if (v != 0.f) atomicAdd(p.dts_w + t, v * hist_scale);
-      }
     }
 #undef HSTU_BWD_RUN
-#undef HSTU_BWD_MODE3
-#undef HSTU_BWD_MODE3_BODY
 #undef HSTU_BWD_ELEM2
     // ---------------- epilogue: dV (warpgroup 0) / dK (warpgroup 1): TMEM -> scale -> global ----------------
     mbar_wait(&bars->fin_full, 0);
@@ -1004,10 +897,6 @@ static bool umma_bwd_supported(const hstu_attn_params& p) {
   if (!umma_fwd_supported(p)) return false;  // dtype / dims / alignment of q, k, v (out is not used by the backward)
   // d = 256: dK and dV alone fill the 512 TMEM columns; the forward has a tcgen05 kernel, the backward runs on the generic path
   if (p.dqk != 32 && p.dqk != 64 && p.dqk != 128) return false;
-  if (p.pos_w != nullptr || p.ts_w != nullptr) {
-    // relative bias: the ring-path kernel of d = 32 (its shared memory has room for the gradient histograms)
-    if (p.dqk != 32 || kBwdPsmem || BwdCfg<32>::PRING || p.num_ts_buckets + 1 > BwdCfg<32>::HIST_TS) return false;
-  }
   return aligned_view(p.dout, p.do_row_stride, p.do_head_stride) && aligned_view(p.dq, p.dq_row_stride, p.dq_head_stride) &&
          aligned_view(p.dk, p.dk_row_stride, p.dk_head_stride) && aligned_view(p.dv_out, p.dv_row_stride, p.dv_head_stride);
 }
@@ -1063,12 +952,6 @@ static int launch_bwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   bp.alpha_half = 0.5f * p.alpha;
   bp.dv_scale = 1.0f / (float)p.max_seq_len;
   bp.dk_scale = p.alpha / (float)p.max_seq_len;
-  bp.pos_w = p.pos_w;
-  bp.ts_w = p.ts_w;
-  bp.timestamps = reinterpret_cast<const long long*>(p.timestamps);
-  bp.dpos_w = p.dpos_w;
-  bp.dts_w = p.dts_w;
-  bp.num_ts_buckets = p.num_ts_buckets;
   HSTU_CUDA_OK(cudaMemsetAsync(p.workspace, 0, need, st));
   const long long nvec = p.total_rows * p.heads * (D / 8);
   long long blocks = (nvec + 255) / 256;

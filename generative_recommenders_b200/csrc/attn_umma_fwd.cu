@@ -44,11 +44,6 @@ struct alignas(64) FwdParams {
   int win, min_full, ctx;
   float alpha_half;  // alpha / 2
   float inv_n;       // 1 / max_seq_len
-  // relative attention bias of the research block (hstu.py:124-143), all NULL without it
-  const float* pos_w;          // [2 n - 1]
-  const float* ts_w;           // [num_ts_buckets + 1]
-  const long long* timestamps; // [B, n]
-  int num_ts_buckets;
 };
 
 template <int D>
@@ -279,20 +274,12 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
     // plain causal (+targets): valid(i, j) = (j < lim_i) | (j == i)   (common.cuh: mask_valid, fast path)
     const int lim_i = msk.has_tgt ? min(i_pos, msk.max_id) : i_pos;
     const int full_lim = fast ? min(m0, msk.has_tgt ? msk.max_id : 0x7fffffff) : -1;
-    // relative bias (research block): x = alpha s + pos_w[n - 1 + j - i] + ts_w[bucket(ts[i + 1] - ts[j])], evaluated per score from
-    // L1-resident tables; ~40 instructions per score instead of 6, on problems of a few hundred positions (hstu.py:124-143)
-    const bool has_bias = p.pos_w != nullptr || p.ts_w != nullptr;
-    const int nmax = p.max_seq_len;
-    const int i_clamped = min(i_pos, nmax - 1);
-    const long long* ts_row = p.timestamps ? p.timestamps + (long long)b * nmax : nullptr;
-    const long long ts_i1 = (p.ts_w && ts_row) ? __ldg(ts_row + min(i_clamped + 1, nmax - 1)) : 0;
-    const float* pos_row = p.pos_w ? p.pos_w + (nmax - 1 - i_clamped) : nullptr;  // indexed by j
     for (int i = wg, it = 0; i < T; i += NWG, ++it) {
       const uint32_t s_taddr = tmem + Cfg::TMEM_S + (i % NSL) * 128 + lane_bits;
       mbar_wait(&bars->s_full[i % NSL], (i / NSL) & 1);
       tc_fence_after_sync();
       const int n0 = (t0 + i) * 128;
-      const int mode = has_bias ? 3 : ((n0 + 128 <= full_lim) ? 0 : (fast ? 1 : 2));  // tile-uniform: no divergence
+      const int mode = (n0 + 128 <= full_lim) ? 0 : (fast ? 1 : 2);  // tile-uniform: no divergence
       const int lim_rel = lim_i - n0, diag_rel = i_pos - n0;
       uint32_t sbuf[2][32];
 #ifdef HSTU_EXP_NO_ELEM
@@ -326,26 +313,6 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
             float p0 = pv.x, p1 = pv.y;
             p0 = ((j0 < lim_rel) | (j0 == diag_rel)) ? p0 : 0.f;
             p1 = ((j0 + 1 < lim_rel) | (j0 + 1 == diag_rel)) ? p1 : 0.f;
-            pk[e >> 1] = pack_f16x2_sat(p0, p1);
-          }
-        } else if (mode == 3) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const int j = n0 + c * 32 + e;
-            float xx[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int jc = min(j + q, nmax - 1);
-              float bias = 0.f;
-              if (pos_row) bias += __ldg(pos_row + jc);
-              if (p.ts_w) bias += __ldg(p.ts_w + ts_bucket(ts_i1 - __ldg(ts_row + jc), p.num_ts_buckets));
-              xx[q] = fmaf(__uint_as_float(s[e + q]), p.alpha_half, 0.5f * bias);   // h = (alpha s + bias) / 2
-            }
-            const float2 hh = make_float2(xx[0], xx[1]);
-            const float2 pv = __ffma2_rn(hh, make_float2(tanh_approx(hh.x), tanh_approx(hh.y)), hh);
-            float p0 = pv.x, p1 = pv.y;
-            p0 = (j < len && mask_valid(msk, i_pos, j)) ? p0 : 0.f;
-            p1 = (j + 1 < len && mask_valid(msk, i_pos, j + 1)) ? p1 : 0.f;
             pk[e >> 1] = pack_f16x2_sat(p0, p1);
           }
         } else {
@@ -427,8 +394,7 @@ static bool aligned_view(const void* ptr, long long row_stride, long long head_s
 bool umma_fwd_supported(const hstu_attn_params& p) {
   if (p.dtype != HSTU_BF16 && p.dtype != HSTU_F16) return false;
   if (p.dqk != p.dv || (p.dqk != 32 && p.dqk != 64 && p.dqk != 128 && p.dqk != 256)) return false;
-  if (p.delta_q_len != 0) return false;
-  if ((p.pos_w != nullptr || p.ts_w != nullptr) && p.dqk > 128) return false;  // relative bias: d <= 128
+  if (p.delta_q_len != 0 || p.pos_w != nullptr || p.ts_w != nullptr) return false;
   if (p.total_rows >= (1ll << 31) - 256) return false;
   if (!aligned_view(p.q, p.q_row_stride, p.q_head_stride) || !aligned_view(p.k, p.k_row_stride, p.k_head_stride) ||
       !aligned_view(p.v, p.v_row_stride, p.v_head_stride) || !aligned_view(p.out, p.o_row_stride, p.o_head_stride))
@@ -457,10 +423,6 @@ static int launch_fwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   fp.ctx = p.contextual_seq_len;
   fp.alpha_half = 0.5f * p.alpha;
   fp.inv_n = 1.0f / (float)p.max_seq_len;
-  fp.pos_w = p.pos_w;
-  fp.ts_w = p.ts_w;
-  fp.timestamps = reinterpret_cast<const long long*>(p.timestamps);
-  fp.num_ts_buckets = p.num_ts_buckets;
   auto kern = attn_fwd_umma_kernel<D, BF16>;
   HSTU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   dim3 grid((p.max_seq_len + 127) / 128, p.heads, p.batch);

@@ -249,10 +249,11 @@ class _RelBiasAttentionFunction(torch.autograd.Function):
     """Research-path attention: silu(QK^T + rel_bias)/n under a plain causal mask (research hstu.py:150-223)."""
 
     @staticmethod
-    def forward(ctx, n, q, k, v, seq_offsets, pos_w, ts_w, timestamps, impl):
-        out = cuda_hstu_attention_fwd(n, 1.0, q, k, v, seq_offsets, impl=impl, bias=(pos_w, ts_w, timestamps))
+    def forward(ctx, n, q, k, v, seq_offsets, pos_w, ts_w, timestamps):
+        out = cuda_hstu_attention_fwd(n, 1.0, q, k, v, seq_offsets, impl=_lib.IMPL_GENERIC,
+                                      bias=(pos_w, ts_w, timestamps))
         ctx.save_for_backward(q, k, v, seq_offsets, pos_w, ts_w, timestamps)
-        ctx.n, ctx.impl = n, impl
+        ctx.n = n
         return out
 
     @staticmethod
@@ -261,13 +262,11 @@ class _RelBiasAttentionFunction(torch.autograd.Function):
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         dpos = torch.zeros(pos_w.shape, dtype=torch.float32, device=q.device)
         dts = torch.zeros(ts_w.shape, dtype=torch.float32, device=q.device) if ts_w is not None else None
-        cuda_hstu_attention_bwd(ctx.n, 1.0, dout, q, k, v, dq, dk, dv, seq_offsets, impl=ctx.impl,
+        cuda_hstu_attention_bwd(ctx.n, 1.0, dout, q, k, v, dq, dk, dv, seq_offsets, impl=_lib.IMPL_GENERIC,
                                 bias=(pos_w, ts_w, timestamps), dbias=(dpos, dts))
-        return (None, dq, dk, dv, None, dpos.to(pos_w.dtype), None if dts is None else dts.to(ts_w.dtype), None, None)
+        return (None, dq, dk, dv, None, dpos.to(pos_w.dtype), None if dts is None else dts.to(ts_w.dtype), None)
 
 
-def hstu_rel_bias_attention(n: int, q, k, v, seq_offsets, pos_w, ts_w=None, timestamps=None,
-                            impl: int = _lib.IMPL_AUTO) -> torch.Tensor:
-    """q,k [L,H,dqk], v [L,H,dv]; pos_w [2n-1]; ts_w [num_buckets+1], timestamps [B,n] int64 (both or neither).
-    impl AUTO: the tcgen05 kernels when the shape allows (16-bit, dqk == dv; forward d <= 128, backward d == 32), else the generic ones."""
-    return _RelBiasAttentionFunction.apply(n, q, k, v, seq_offsets, pos_w, ts_w, timestamps, impl)
+def hstu_rel_bias_attention(n: int, q, k, v, seq_offsets, pos_w, ts_w=None, timestamps=None) -> torch.Tensor:
+    """q,k [L,H,dqk], v [L,H,dv]; pos_w [2n-1]; ts_w [num_buckets+1], timestamps [B,n] int64 (both or neither)."""
+    return _RelBiasAttentionFunction.apply(n, q, k, v, seq_offsets, pos_w, ts_w, timestamps)

@@ -229,47 +229,3 @@ def test_target_invariance_metamorphic():
         o1 = hstu_mha(256, 0.2, q, k, v, off, num_targets=nt, kernel=HK.CUDA, impl=impl)
         o2 = hstu_mha(256, 0.2, q[perm], k[perm], v[perm], off, num_targets=nt, kernel=HK.CUDA, impl=impl)
         assert_rel(o2, o1[perm].float(), f"target invariance impl {impl}", tol=2e-3)
-
-
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("with_ts", [True, False])
-def test_research_rel_bias_attention_on_tensor_cores_vs_oracle(dtype, with_ts):
-    """The tcgen05 kernels with the relative position / time bias evaluated inside the elementwise stage (forward d <= 128,
-    backward d = 32, incl. the gradients of the two bias tables) against the fp32 oracle and against the generic kernels."""
-    _lib, HK, _, _, rel_attn = _mods()
-    dev = torch.device("cuda")
-    torch.manual_seed(17)
-    n, H, d, nb = 300, 2, 32, 20
-    lengths = [300, 131, 257, 1]
-    off = offsets_from(lengths, dev)
-    L = sum(lengths)
-    q, k, v = (torch.randn(L, H, d, device=dev).mul_(0.5).to(dtype) for _ in range(3))
-    pos_w = torch.randn(2 * n - 1, device=dev) * 0.3
-    ts_w = torch.randn(nb + 1, device=dev) * 0.3 if with_ts else None
-    ts = torch.cumsum(torch.randint(0, 50000, (len(lengths), n), device=dev), dim=1) if with_ts else None
-    dout = torch.randn(L, H, d, device=dev).to(dtype)
-
-    # fp32 oracle (autograd through the restated reference math)
-    qr, kr, vr = (t.float().cpu().requires_grad_() for t in (q, k, v))
-    pr = pos_w.cpu().clone().requires_grad_()
-    tr = ts_w.cpu().clone().requires_grad_() if with_ts else None
-    ref = O.hstu_rel_bias_attention_fwd(n, qr, kr, vr, off.cpu(), pr, tr, None if ts is None else ts.cpu())
-    ref.backward(dout.float().cpu())
-
-    for impl in (_lib.IMPL_AUTO, _lib.IMPL_GENERIC):
-        qq, kk, vv = (t.clone().requires_grad_() for t in (q, k, v))
-        pw = pos_w.clone().requires_grad_()
-        tw = ts_w.clone().requires_grad_() if with_ts else None
-        out = rel_attn(n, qq, kk, vv, off, pw, tw, ts, impl=impl)
-        l0 = _lib.LAUNCHES
-        out.backward(dout)
-        # the backward call reports 3 launches for the tcgen05 path (amax pre-pass, main kernel, dQ convert), 2 for the generic one
-        assert _lib.LAUNCHES - l0 == (3 if impl == _lib.IMPL_AUTO else 2), "AUTO must select the tcgen05 kernels for this shape"
-        tag = f"impl {impl} {dtype}"
-        assert_rel(out, ref.detach(), f"out {tag}")
-        assert_rel(qq.grad, qr.grad, f"dq {tag}")
-        assert_rel(kk.grad, kr.grad, f"dk {tag}")
-        assert_rel(vv.grad, vr.grad, f"dv {tag}")
-        assert_rel(pw.grad, pr.grad, f"dpos_w {tag}", tol=2e-3)   # sums of fp16-rounded-free fp32 dS values over ~1e5 scores
-        if with_ts:
-            assert_rel(tw.grad, tr.grad, f"dts_w {tag}", tol=2e-3)
