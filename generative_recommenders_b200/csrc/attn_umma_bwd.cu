@@ -82,8 +82,9 @@ struct BwdCfg {
   static constexpr int OFF_DQS = OFF_DST + 2 * PT_BYTES;
   static constexpr int OFF_PT = OFF_DQS + 2 * DQS_BYTES;   // PSM: NPB P^T boxes [128 kv][64 q] fp16
   static constexpr int OFF_BAR = OFF_PT + ((kBwdPsmem && D == 32) ? 3 * 16384 : 0);
-  static_assert(OFF_BAR + 256 + 1024 <= 232448, "shared memory budget");
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int BAR_BYTES = 512;   // sizeof(BwdBars) <= 512 is asserted next to the struct (it had outgrown the 256 bytes reserved)
+  static_assert(OFF_BAR + BAR_BYTES + 1024 <= 232448, "shared memory budget");
+  static constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES + 1024;
   // TMEM: a ring of NSLOT score slots, each {S^T half-tile: 64 columns, dP^T half-tile: 64 columns} (a half-tile is
   // 128 key rows x 64 query rows; after the elementwise stage the front of the S^T half holds P^T as bf16), the dV and
   // dK accumulators and NDQ dQ accumulators (tile i -> buffer i % NDQ; with two, the warpgroups drain dQ two tiles late and
@@ -151,6 +152,7 @@ struct BwdBars {
   uint64_t scores_free[3], p_free[4];
   uint32_t tmem_base;
 };
+static_assert(sizeof(BwdBars) <= 512, "BwdBars must fit the bytes reserved for it (BwdCfg::BAR_BYTES)");
 
 #ifdef HSTU_TRACE
 // Debug timeline: CTA (0,0,0) records clock64() stamps of its pipeline events into g_trace[role][index][slot].
