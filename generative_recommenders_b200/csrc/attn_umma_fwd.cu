@@ -46,6 +46,12 @@ struct alignas(64) FwdParams {
   float inv_n;       // 1 / max_seq_len
 };
 
+#ifdef HSTU_FWD_PSMEM
+constexpr bool kFwdPsmem = true;
+#else
+constexpr bool kFwdPsmem = false;
+#endif
+
 template <int D>
 struct FwdCfg {
   static constexpr int SW = (D * 2 >= 128) ? 128 : D * 2;  // swizzle width (bytes) of the Q/K/V boxes
@@ -61,7 +67,14 @@ struct FwdCfg {
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + TILE_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_V + STAGES * TILE_BYTES;
+  // PSM (d <= 64): P goes to shared memory (three boxes of [128 q][128 keys] fp16, K-major, 128-byte swizzle: the A operand of an SS
+  // P.V GEMM) instead of back into its score slot.  The slot then returns to the score issuer as soon as the silu warpgroup has
+  // LOADED it (slot_free) instead of after the P.V GEMM of the tile: the serial chain Q K^T -> silu -> P V -> Q K^T of a slot -- what
+  // bounds this kernel at d = 32 (profiles/r02_ablations.txt) -- loses its last two links.
+  static constexpr bool PSM = kFwdPsmem && D <= 64;
+  static constexpr int P_BYTES = 128 * 128 * 2;            // two 128-byte-swizzle boxes of 64 keys
+  static constexpr int OFF_P = OFF_V + STAGES * TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_P + (PSM ? 3 * P_BYTES : 0);
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
   // ring of 3 score slots of 128 columns; P (bf16 pairs, 64 columns) overwrites the front of its own S slot
   static constexpr int TMEM_S = 0;
@@ -79,6 +92,7 @@ struct FwdBars {
   uint64_t k_full[3], v_full[3];
   uint64_t v_ready[3];  // bf16 inputs: the V tile has been converted to fp16 (128 converter threads)
   uint64_t s_full[3], p_full[3], pv_done[3];
+  uint64_t slot_free[3];  // PSM: the silu warpgroup has loaded the scores of the tile out of the slot (128 arrivals)
   uint64_t o_full;
   uint32_t tmem_base;
 };
@@ -123,6 +137,7 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
   uint8_t* sQ = smem + Cfg::OFF_Q;
   uint8_t* sK = smem + Cfg::OFF_K;
   uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sP = smem + Cfg::OFF_P;   // PSM only
   FwdBars* bars = reinterpret_cast<FwdBars*>(smem + Cfg::OFF_BAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -134,6 +149,7 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
       mbar_init(&bars->s_full[i], 1);
       mbar_init(&bars->p_full[i], 128);
       mbar_init(&bars->pv_done[i], 1);
+      mbar_init(&bars->slot_free[i], 128);
       mbar_init(&bars->v_ready[i], 128);
     }
     mbar_init(&bars->o_full, 1);
@@ -221,7 +237,10 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
     mbar_wait(q_rdy, 0);
     for (int i = 0; i < T; ++i) {
       const int st = i % NST, sl = i % NSL;
-      if (i >= NSL) mbar_wait(&bars->pv_done[sl], ((i / NSL) - 1) & 1);  // P_{i-NSL} (front of this slot) has been consumed
+      if (i >= NSL) {
+        if constexpr (Cfg::PSM) mbar_wait(&bars->slot_free[sl], ((i / NSL) - 1) & 1);  // S_{i-NSL} has been loaded out of this slot
+        else mbar_wait(&bars->pv_done[sl], ((i / NSL) - 1) & 1);                        // P_{i-NSL} (front of this slot) has been consumed
+      }
       mbar_wait(&k_rdy[st], (i / NST) & 1);
       tc_fence_after_sync();
       const uint64_t kd = dk0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
@@ -250,10 +269,19 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
       const uint64_t vd = dv0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
       const uint32_t tp = tmem + Cfg::TMEM_S + sl * 128;
       if (leader) {
+        if constexpr (Cfg::PSM) {
+          // A = P box sl in shared memory: [128 q][64 keys] x 2 boxes, K-major; k-step ks = 16 keys = 32 bytes inside the 128-byte row
+          const uint64_t pd = desc_kmajor<128>(smem_u32(sP), 0) + (uint64_t)((sl * Cfg::P_BYTES) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            mma_ss(tmem + Cfg::TMEM_O + (ks % Cfg::NACC) * D, pd + (uint64_t)(((ks >> 2) * 16384 + (ks & 3) * 32) >> 4),
+                   vd + (uint64_t)((ks * 16 * SW) >> 4), idesc_pv, (i > 0) || (ks >= Cfg::NACC));
+        } else {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)  // 16 bf16 of K per 8 TMEM columns
           mma_ts(tmem + Cfg::TMEM_O + (ks % Cfg::NACC) * D, tp + ks * 8, vd + (uint64_t)((ks * 16 * SW) >> 4), idesc_pv,
                  (i > 0) || (ks >= Cfg::NACC));
+        }
         mma_commit(&bars->pv_done[sl]);
       }
       __syncwarp();
@@ -294,6 +322,12 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
 #endif
         tmem_ld_wait();
         if (c < 3) tmem_ld32(s_taddr + (c + 1) * 32, sbuf[(c + 1) & 1]);  // prefetch the next 32 columns
+        if constexpr (Cfg::PSM) {
+          if (c == 3) {                      // the last chunk is in registers: the slot goes back to the score issuer
+            tc_fence_before_sync();
+            mbar_arrive(&bars->slot_free[i % NSL]);
+          }
+        }
         const uint32_t(&s)[32] = sbuf[c & 1];
         uint32_t pk[16];
         if (mode == 0) {
@@ -327,12 +361,25 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
             pk[e >> 1] = pack_f16x2_sat(p0, p1);
           }
         }
+        if constexpr (Cfg::PSM) {
+          if (c == 0 && i >= NSL) mbar_wait(&bars->pv_done[i % NSL], ((i / NSL) - 1) & 1);  // P V of tile i - 3 has read this P box
+          // P chunk c = keys [32 c, 32 c + 32) of this thread's query row: four 16-byte pieces of box c / 2
+          const uint32_t pbox = smem_u32(sP + (i % NSL) * Cfg::P_BYTES + (c >> 1) * 16384);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            st_shared_v4(pbox + swizzled_chunk_offset<128>(row, (c & 1) * 4 + j4), pk[4 * j4], pk[4 * j4 + 1], pk[4 * j4 + 2], pk[4 * j4 + 3]);
+        } else {
         // P chunk c (32 bf16 = 16 columns) goes to columns [16 c, 16 c + 16) of the slot: a region of S that has already
         // been read (S chunk c covers columns [32 c, 32 c + 32))
         tmem_st16(s_taddr + c * 16, pk);
+        }
       }
-      tmem_st_wait();
-      tc_fence_before_sync();
+      if constexpr (Cfg::PSM) {
+        fence_proxy_async_smem();
+      } else {
+        tmem_st_wait();
+        tc_fence_before_sync();
+      }
       mbar_arrive(&bars->p_full[i % NSL]);
     }
     // ---------------- epilogue: O (TMEM) -> * 1/N -> global ----------------
