@@ -44,6 +44,7 @@ struct alignas(64) FwdParams {
   int win, min_full, ctx;
   float alpha_half;  // alpha / 2
   float inv_n;       // 1 / max_seq_len
+  int heads, batch;  // persistent kernel: the work items are enumerated inside the kernel
 };
 
 #ifdef HSTU_FWD_PSMEM
@@ -421,6 +422,392 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
+
+#ifdef HSTU_FWD_PERSIST
+// ------------------------------------------------------------------------------------------------
+// Persistent forward (d <= 64, opt-in): ONE CTA per SM walks a static list of work items (query tile, head, sequence), heavy tiles
+// first.  TMEM is allocated and the barriers are initialised once; the K / V rings, the score slots and the barrier phases run on
+// a GLOBAL key-tile counter, so the loads and score GEMMs of item k + 1 start while item k is still in its silu / P.V / epilogue
+// phase.  Q has two buffers (q_full / q_empty), O two TMEM accumulator sets (o_full / o_empty) for the same reason.  Short sequences
+// (a handful of key tiles per item) otherwise pay TMEM allocation, barrier set-up, the first TMA round trip, the pipeline drain and
+// the epilogue once per CTA with nothing to overlap them: ~5 us per item against ~1 us of work at Lmax = 512.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+struct FwdPCfg {
+  using C = FwdCfg<D>;
+  static constexpr int OFF_Q = 0;                                   // two Q buffers
+  static constexpr int OFF_K = OFF_Q + 2 * C::TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + 3 * C::TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_V + 3 * C::TILE_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static constexpr int NACC = (D <= 32) ? 2 : 1;                    // per O buffer
+  static constexpr int TMEM_O = 3 * 128;                            // buffer b: columns [TMEM_O + 64 b, + 64)
+  static_assert(D <= 64 && NACC * D == 64, "two O buffers of 64 columns");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+struct FwdPBars {
+  uint64_t q_full[2], q_empty[2];
+  uint64_t k_full[3], v_full[3], v_ready[3];
+  uint64_t s_full[3], p_full[3], pv_done[3];
+  uint64_t o_full[2], o_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(FwdPBars) <= 512, "barrier block");
+
+struct FwdItem {
+  int b, h, m0, len, len_true, T, t0, mrows;
+  long long row0;
+  SeqMask msk;
+};
+
+// item k of the static list: query tiles in descending order (heavy first), then (sequence, head)
+__device__ __forceinline__ FwdItem fwd_item(const FwdParams& p, long long k, int ntiles) {
+  FwdItem it;
+  const int hb = p.heads * p.batch;
+  const int qt = ntiles - 1 - (int)(k / hb);
+  const int r = (int)(k % hb);
+  it.h = r % p.heads;
+  it.b = r / p.heads;
+  it.m0 = qt * 128;
+  it.row0 = load_index(p.seq_offsets, p.offsets_i64, it.b);
+  it.len_true = (int)(load_index(p.seq_offsets, p.offsets_i64, it.b + 1) - it.row0);
+  it.len = min(it.len_true, p.max_seq_len);
+  it.T = 0;
+  it.t0 = 0;
+  it.mrows = 0;
+  if (it.m0 < it.len) {
+    const int n_tgt = p.num_targets ? (int)load_index(p.num_targets, p.targets_i64, it.b) : -1;
+    it.msk = make_seq_mask(it.len, n_tgt, p.win, p.min_full, p.ctx);
+    it.mrows = min(128, it.len - it.m0);
+    int lo, hi;
+    kv_range_for_q_rows(it.msk, it.m0, it.m0 + it.mrows, &lo, &hi);
+    it.t0 = lo / 128;
+    it.T = (hi + 127) / 128 - it.t0;
+  }
+  return it;
+}
+
+template <int D, bool BF16>
+__global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_persist_kernel(const __grid_constant__ FwdParams p) {
+  using Cfg = FwdCfg<D>;
+  using PC = FwdPCfg<D>;
+  constexpr bool CONV = BF16;
+  constexpr int SW = Cfg::SW;
+  const int ntiles = (p.max_seq_len + 127) / 128;
+  const long long n_items = (long long)ntiles * p.heads * p.batch;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + PC::OFF_Q;
+  uint8_t* sK = smem + PC::OFF_K;
+  uint8_t* sV = smem + PC::OFF_V;
+  FwdPBars* bars = reinterpret_cast<FwdPBars*>(smem + PC::OFF_BAR);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->q_full[i], 1);
+      mbar_init(&bars->q_empty[i], 1);
+      mbar_init(&bars->o_full[i], 1);
+      mbar_init(&bars->o_empty[i], 256);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bars->k_full[i], 1);
+      mbar_init(&bars->v_full[i], 1);
+      mbar_init(&bars->v_ready[i], 128);
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->p_full[i], 128);
+      mbar_init(&bars->pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = bars->tmem_base;
+  uint64_t* const v_rdy = CONV ? bars->v_ready : bars->v_full;
+
+  // every role walks the same item list with the same two counters: g0 = key tiles before this item, n = non-empty items before it
+  if (warp >= 12) {
+    reg_dealloc<64>();
+    const int t = tid - 384;
+    int g0 = 0;
+    for (long long k = blockIdx.x; k < n_items; k += gridDim.x) {
+      const FwdItem it = fwd_item(p, k, ntiles);
+      for (int i = 0; i < it.T; ++i) {
+        const int g = g0 + i, st = g % 3;
+        mbar_wait(&bars->v_full[st], (g / 3) & 1);
+        convert_bf16_to_f16_inplace<128>(sV + st * Cfg::TILE_BYTES, Cfg::TILE_BYTES, t, 1.0f);
+        fence_proxy_async_smem();
+        mbar_arrive(&bars->v_ready[st]);
+      }
+      g0 += it.T;
+    }
+  } else if (warp < 4) {
+    if (CONV) reg_dealloc<80>();
+    if (warp == 0) {
+      if (lane == 0) {
+        // ---------------- TMA producer: Q of every item, K tiles ----------------
+        prefetch_tensormap(&p.tmQ);
+        prefetch_tensormap(&p.tmK);
+        int g0 = 0, n = 0;
+        for (long long k = blockIdx.x; k < n_items; k += gridDim.x) {
+          const FwdItem it = fwd_item(p, k, ntiles);
+          if (it.T == 0) continue;
+          const int qb = n & 1;
+          if (n >= 2) mbar_wait(&bars->q_empty[qb], ((n >> 1) - 1) & 1);   // the score GEMMs of item n - 2 have read this buffer
+          mbar_arrive_expect_tx(&bars->q_full[qb], Cfg::TILE_BYTES);
+#pragma unroll
+          for (int bx = 0; bx < Cfg::NBOX; ++bx)
+            tma_load_3d(sQ + qb * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, &p.tmQ, &bars->q_full[qb], bx * Cfg::BOX_COLS, it.h,
+                        (int)(it.row0 + it.m0));
+          for (int i = 0; i < it.T; ++i) {
+            const int g = g0 + i, st = g % 3;
+            if (g >= 3) mbar_wait(&bars->s_full[st], ((g / 3) - 1) & 1);    // Q K^T of key tile g - 3 has consumed this stage
+            mbar_arrive_expect_tx(&bars->k_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+            for (int bx = 0; bx < Cfg::NBOX; ++bx)
+              tma_load_3d(sK + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, &p.tmK, &bars->k_full[st], bx * Cfg::BOX_COLS, it.h,
+                          (int)(it.row0 + (long long)(it.t0 + i) * 128));
+          }
+          g0 += it.T;
+          ++n;
+        }
+      }
+    } else if (warp == 3) {
+      if (lane == 0) {
+        // ---------------- TMA producer: V tiles ----------------
+        prefetch_tensormap(&p.tmV);
+        int g0 = 0;
+        for (long long k = blockIdx.x; k < n_items; k += gridDim.x) {
+          const FwdItem it = fwd_item(p, k, ntiles);
+          for (int i = 0; i < it.T; ++i) {
+            const int g = g0 + i, st = g % 3;
+            if (g >= 3) mbar_wait(&bars->pv_done[st], ((g / 3) - 1) & 1);   // P V of key tile g - 3 has consumed this stage
+            mbar_arrive_expect_tx(&bars->v_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+            for (int bx = 0; bx < Cfg::NBOX; ++bx)
+              tma_load_3d(sV + st * Cfg::TILE_BYTES + bx * Cfg::BOX_BYTES, &p.tmV, &bars->v_full[st], bx * Cfg::BOX_COLS, it.h,
+                          (int)(it.row0 + (long long)(it.t0 + i) * 128));
+          }
+          g0 += it.T;
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------- MMA issuer 1: S = Q K^T of every key tile of every item ----------------
+      const bool leader = lane == 0;
+      constexpr uint32_t idesc_qk = make_idesc(128, 128, false, false, BF16, BF16);
+      const uint64_t dq0 = desc_kmajor<SW>(smem_u32(sQ), 0);
+      const uint64_t dk0 = desc_kmajor<SW>(smem_u32(sK), 0);
+      int g0 = 0, n = 0;
+      for (long long k = blockIdx.x; k < n_items; k += gridDim.x) {
+        const FwdItem it = fwd_item(p, k, ntiles);
+        if (it.T == 0) continue;
+        const int qb = n & 1;
+        mbar_wait(&bars->q_full[qb], (n >> 1) & 1);
+        const uint64_t qd = dq0 + (uint64_t)((qb * Cfg::TILE_BYTES) >> 4);
+        for (int i = 0; i < it.T; ++i) {
+          const int g = g0 + i, st = g % 3;
+          if (g >= 3) mbar_wait(&bars->pv_done[st], ((g / 3) - 1) & 1);     // P of key tile g - 3 (front of this slot) has been consumed
+          mbar_wait(&bars->k_full[st], (g / 3) & 1);
+          tc_fence_after_sync();
+          const uint64_t kd = dk0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
+          const uint32_t ts = tmem + st * 128;
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks) {
+              const uint32_t kb = ks * 32, bx = kb / SW, off = kb % SW;
+              const uint64_t o = (uint64_t)((bx * Cfg::BOX_BYTES + off) >> 4);
+              mma_ss(ts, qd + o, kd + o, idesc_qk, ks > 0);
+            }
+            mma_commit(&bars->s_full[st]);
+            if (i == it.T - 1) mma_commit(&bars->q_empty[qb]);               // every score GEMM of this item has read Q
+          }
+          __syncwarp();
+        }
+        g0 += it.T;
+        ++n;
+      }
+    } else {
+      // ---------------- MMA issuer 2: O += P V ----------------
+      const bool leader = lane == 0;
+      constexpr uint32_t idesc_pv = make_idesc(128, D, false, true, false, false);
+      const uint64_t dv0 = desc_mnmajor<SW>(smem_u32(sV), 0, Cfg::BOX_BYTES);
+      int g0 = 0, n = 0;
+      for (long long k = blockIdx.x; k < n_items; k += gridDim.x) {
+        const FwdItem it = fwd_item(p, k, ntiles);
+        if (it.T == 0) continue;
+        const int ob = n & 1;
+        if (n >= 2) {                                                        // the epilogue of item n - 2 has read this O buffer
+          mbar_wait(&bars->o_empty[ob], ((n >> 1) - 1) & 1);
+          tc_fence_after_sync();
+        }
+        for (int i = 0; i < it.T; ++i) {
+          const int g = g0 + i, st = g % 3;
+          mbar_wait(&bars->p_full[st], (g / 3) & 1);
+          mbar_wait(&v_rdy[st], (g / 3) & 1);
+          tc_fence_after_sync();
+          const uint64_t vd = dv0 + (uint64_t)((st * Cfg::TILE_BYTES) >> 4);
+          const uint32_t tp = tmem + st * 128;
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              mma_ts(tmem + PC::TMEM_O + ob * 64 + (ks % PC::NACC) * D, tp + ks * 8, vd + (uint64_t)((ks * 16 * SW) >> 4), idesc_pv,
+                     (i > 0) || (ks >= PC::NACC));
+            mma_commit(&bars->pv_done[st]);
+            if (i == it.T - 1) mma_commit(&bars->o_full[ob]);
+          }
+          __syncwarp();
+        }
+        g0 += it.T;
+        ++n;
+      }
+    }
+  } else {
+    // ---------------- silu warpgroups: key tiles with (global index) % 2 == wg; then half of the O tile each ----------------
+    if (CONV) reg_alloc<168>();
+    const int wg = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
+    const float2 ah2 = make_float2(p.alpha_half, p.alpha_half);
+    int g0 = 0, n = 0;
+    for (long long k = blockIdx.x; k < n_items; k += gridDim.x) {
+      const FwdItem it = fwd_item(p, k, ntiles);
+      if (it.m0 == 0 && it.len_true > it.len) {
+        // rows of this sequence beyond max_seq_len: zeros (the lightest query tile of every (sequence, head) does it)
+        const long long nz = (long long)(it.len_true - it.len) * D;
+        uint16_t* ob = reinterpret_cast<uint16_t*>(p.out);
+        for (long long idx = tid - 128; idx < nz; idx += 256) {
+          const long long r = it.row0 + it.len + idx / D;
+          ob[r * p.o_row_stride + (long long)it.h * p.o_head_stride + idx % D] = 0;
+        }
+      }
+      if (it.T == 0) continue;
+      const SeqMask msk = it.msk;
+      const int m0 = it.m0, len = it.len;
+      const int i_pos = m0 + row;
+      const bool fast = msk.fast != 0;
+      const int lim_i = msk.has_tgt ? min(i_pos, msk.max_id) : i_pos;
+      const int full_lim = fast ? min(m0, msk.has_tgt ? msk.max_id : 0x7fffffff) : -1;
+      for (int i = 0; i < it.T; ++i) {
+        const int g = g0 + i;
+        if ((g & 1) != wg) continue;
+        const int st = g % 3;
+        const uint32_t s_taddr = tmem + st * 128 + lane_bits;
+        mbar_wait(&bars->s_full[st], (g / 3) & 1);
+        tc_fence_after_sync();
+        const int n0 = (it.t0 + i) * 128;
+        const int mode = (n0 + 128 <= full_lim) ? 0 : (fast ? 1 : 2);
+        const int lim_rel = lim_i - n0, diag_rel = i_pos - n0;
+        uint32_t sbuf[2][32];
+        tmem_ld32(s_taddr, sbuf[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld32(s_taddr + (c + 1) * 32, sbuf[(c + 1) & 1]);
+          const uint32_t(&s)[32] = sbuf[c & 1];
+          uint32_t pk[16];
+          if (mode == 0) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), ah2);
+              const float2 pv = __ffma2_rn(hh, make_float2(tanh_approx(hh.x), tanh_approx(hh.y)), hh);
+              pk[e >> 1] = pack_f16x2_sat(pv.x, pv.y);
+            }
+          } else if (mode == 1) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const int j0 = c * 32 + e;
+              const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), ah2);
+              const float2 pv = __ffma2_rn(hh, make_float2(tanh_approx(hh.x), tanh_approx(hh.y)), hh);
+              float p0 = pv.x, p1 = pv.y;
+              p0 = ((j0 < lim_rel) | (j0 == diag_rel)) ? p0 : 0.f;
+              p1 = ((j0 + 1 < lim_rel) | (j0 + 1 == diag_rel)) ? p1 : 0.f;
+              pk[e >> 1] = pack_f16x2_sat(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const int j = n0 + c * 32 + e;
+              const float2 hh = __fmul2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), ah2);
+              const float2 pv = __ffma2_rn(hh, make_float2(tanh_approx(hh.x), tanh_approx(hh.y)), hh);
+              float p0 = pv.x, p1 = pv.y;
+              p0 = (j < len && mask_valid(msk, i_pos, j)) ? p0 : 0.f;
+              p1 = (j + 1 < len && mask_valid(msk, i_pos, j + 1)) ? p1 : 0.f;
+              pk[e >> 1] = pack_f16x2_sat(p0, p1);
+            }
+          }
+          tmem_st16(s_taddr + c * 16, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&bars->p_full[st]);
+      }
+      // ---------------- epilogue of this item: O buffer n & 1 -> * 1/N -> global; then hand the buffer back ----------------
+      const int ob = n & 1;
+      mbar_wait(&bars->o_full[ob], (n >> 1) & 1);
+      tc_fence_after_sync();
+      constexpr int HALF = D / 2;
+      const int cbase = wg * HALF;
+      uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + (it.row0 + m0 + row) * p.o_row_stride + (long long)it.h * p.o_head_stride + cbase;
+#pragma unroll
+      for (int c = 0; c < HALF / 16; ++c) {
+        uint32_t o[16];
+        tmem_ld16(tmem + PC::TMEM_O + ob * 64 + cbase + c * 16 + lane_bits, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int a = 1; a < PC::NACC; ++a) {
+          uint32_t o2[16];
+          tmem_ld16(tmem + PC::TMEM_O + ob * 64 + a * D + cbase + c * 16 + lane_bits, o2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) + __uint_as_float(o2[e]));
+        }
+        if (row < it.mrows) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const float a = __uint_as_float(o[e]) * p.inv_n, bb = __uint_as_float(o[e + 1]) * p.inv_n;
+            pk[e >> 1] = BF16 ? pack_bf16x2(a, bb) : pack_f16x2(a, bb);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(orow + c * 16);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&bars->o_empty[ob]);
+      g0 += it.T;
+      ++n;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+template <int D, bool BF16>
+static int launch_fwd_persist(const FwdParams& fp, const hstu_attn_params& p, cudaStream_t st) {
+  using PC = FwdPCfg<D>;
+  auto kern = attn_fwd_umma_persist_kernel<D, BF16>;
+  HSTU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PC::SMEM_BYTES));
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    HSTU_CUDA_OK(cudaGetDevice(&dev));
+    HSTU_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long items = (long long)((p.max_seq_len + 127) / 128) * p.heads * p.batch;
+  const int grid = (int)(items < n_sm ? items : n_sm);
+  kern<<<grid, BF16 ? 512 : 384, PC::SMEM_BYTES, st>>>(fp);
+  HSTU_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+#endif  // HSTU_FWD_PERSIST
+
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
@@ -470,6 +857,11 @@ static int launch_fwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   fp.ctx = p.contextual_seq_len;
   fp.alpha_half = 0.5f * p.alpha;
   fp.inv_n = 1.0f / (float)p.max_seq_len;
+  fp.heads = p.heads;
+  fp.batch = p.batch;
+#ifdef HSTU_FWD_PERSIST
+  if constexpr (D <= 64) return launch_fwd_persist<D, BF16>(fp, p, st);
+#endif
   auto kern = attn_fwd_umma_kernel<D, BF16>;
   HSTU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   dim3 grid((p.max_seq_len + 127) / 128, p.heads, p.batch);
