@@ -423,14 +423,16 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
 }
 
 
-#ifdef HSTU_FWD_PERSIST
 // ------------------------------------------------------------------------------------------------
-// Persistent forward (d <= 64, opt-in): ONE CTA per SM walks a static list of work items (query tile, head, sequence), heavy tiles
+// Persistent forward (d <= 64, max_seq_len <= 4096): ONE CTA per SM walks a static list of work items (query tile, head, sequence), heavy tiles
 // first.  TMEM is allocated and the barriers are initialised once; the K / V rings, the score slots and the barrier phases run on
 // a GLOBAL key-tile counter, so the loads and score GEMMs of item k + 1 start while item k is still in its silu / P.V / epilogue
 // phase.  Q has two buffers (q_full / q_empty), O two TMEM accumulator sets (o_full / o_empty) for the same reason.  Short sequences
 // (a handful of key tiles per item) otherwise pay TMEM allocation, barrier set-up, the first TMA round trip, the pipeline drain and
 // the epilogue once per CTA with nothing to overlap them: ~5 us per item against ~1 us of work at Lmax = 512.
+// Measured on B200 (fwd ms, bf16, one-CTA-per-item kernel -> this one): B 512, H 4, d 64: Lmax 512 0.349 -> 0.267, Lmax 2048 2.179 ->
+// 2.102; B 512, H 4, d 32, Lmax 512: 0.324 -> 0.244; B 128, H 8, d 32, Lmax 256: 0.089 -> 0.062; headline (B 16, H 8, d 32, Lmax 8192):
+// 1.328 -> 1.344, which is why long sequences keep the other kernel (HSTU_FWD_PERSIST=0 / 1 in the environment forces either).
 // ------------------------------------------------------------------------------------------------
 template <int D>
 struct FwdPCfg {
@@ -806,7 +808,6 @@ static int launch_fwd_persist(const FwdParams& fp, const hstu_attn_params& p, cu
   HSTU_CUDA_OK(cudaGetLastError());
   return 0;
 }
-#endif  // HSTU_FWD_PERSIST
 
 // ------------------------------------------------------------------------------------------------
 // host
@@ -859,9 +860,10 @@ static int launch_fwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   fp.inv_n = 1.0f / (float)p.max_seq_len;
   fp.heads = p.heads;
   fp.batch = p.batch;
-#ifdef HSTU_FWD_PERSIST
-  if constexpr (D <= 64) return launch_fwd_persist<D, BF16>(fp, p, st);
-#endif
+  if constexpr (D <= 64) {
+    static const int forced = [] { const char* e = getenv("HSTU_FWD_PERSIST"); return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0); }();
+    if (forced == 1 || (forced < 0 && p.max_seq_len <= 4096)) return launch_fwd_persist<D, BF16>(fp, p, st);
+  }
   auto kern = attn_fwd_umma_kernel<D, BF16>;
   HSTU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   dim3 grid((p.max_seq_len + 127) / 128, p.heads, p.batch);
