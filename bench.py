@@ -347,6 +347,9 @@ def run_ours(args):
                     "hbm_gbs_algorithmic": abytes["fwd"] / (kt["attn_fwd"] * 1e-3) / 1e9},
             "bwd_hbm_gbs_algorithmic": abytes["bwd"] / (kt["attn_bwd"] * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
             "attn_share_of_step": (kt["attn_bwd"] + kt["attn_fwd"]) * per_step_calls / (ms / args.steps),
+            # what bounds the kernel below the tensor peak at this head dim: measured by timing-only ablations, not assumed
+            "bound_evidence": "profiles/r02_ablations.txt (d = 32 backward: tcgen05 issue rate of its N = 32 MMAs, 1464 clk per "
+                              "128 x 128 tile = 0.67 of the bf16 peak for this tiling; forward: serial chain of a TMEM score slot)",
         }
     out["kernel_ms_per_call"] = {k: round(v, 4) for k, v in sorted(kt.items())}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
