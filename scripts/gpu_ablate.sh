@@ -1,4 +1,8 @@
-# timing-only ablations (wrong numerics) of the attention kernels on the headline shape: which stage bounds them?
+# timing-only ablations (wrong numerics) of the attention kernels on the headline shape: build the variants first, e.g.
+#   python scripts/build_variant.py noelem "HSTU_EXP_BWD_NO_ELEM HSTU_EXP_NO_ELEM" attn_umma_bwd.cu,attn_umma_fwd.cu
+#   python scripts/build_variant.py nomufu HSTU_EXP_NO_MUFU attn_umma_bwd.cu,attn_umma_fwd.cu
+#   python scripts/build_variant.py nodrain HSTU_EXP_BWD_NO_DRAIN attn_umma_bwd.cu
+#   gpurun -- bash scripts/gpu_ablate.sh noelem nomufu nodrain
 mkdir -p gpurun_out
 : > gpurun_out/ablate.txt
 for v in default "$@"; do
