@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
 
 
 // ------------------------------------------------------------------------------------------------
-// Persistent forward (d <= 64, max_seq_len <= 4096): ONE CTA per SM walks a static list of work items (query tile, head, sequence), heavy tiles
+// Persistent forward (d <= 128, max_seq_len <= 4096): ONE CTA per SM walks a static list of work items (query tile, head, sequence), heavy tiles
 // first.  TMEM is allocated and the barriers are initialised once; the K / V rings, the score slots and the barrier phases run on
 // a GLOBAL key-tile counter, so the loads and score GEMMs of item k + 1 start while item k is still in its silu / P.V / epilogue
 // phase.  Q has two buffers (q_full / q_empty), O two TMEM accumulator sets (o_full / o_empty) for the same reason.  Short sequences
@@ -437,14 +437,20 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
 template <int D>
 struct FwdPCfg {
   using C = FwdCfg<D>;
-  static constexpr int OFF_Q = 0;                                   // two Q buffers
-  static constexpr int OFF_K = OFF_Q + 2 * C::TILE_BYTES;
+  // d <= 64: two Q buffers and two O accumulator sets of 64 columns; d = 128: one of each (a 128-column O next to the three score
+  // slots fills the tensor memory, two 32 KB Q tiles would not fit the shared memory) -- the next item's K / V loads and score GEMMs
+  // still overlap the current item, its P.V GEMMs wait for the epilogue
+  static constexpr int NQ = (D <= 64) ? 2 : 1;
+  static constexpr int NO = (D <= 64) ? 2 : 1;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + NQ * C::TILE_BYTES;
   static constexpr int OFF_V = OFF_K + 3 * C::TILE_BYTES;
   static constexpr int OFF_BAR = OFF_V + 3 * C::TILE_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
-  static constexpr int NACC = (D <= 32) ? 2 : 1;                    // per O buffer
-  static constexpr int TMEM_O = 3 * 128;                            // buffer b: columns [TMEM_O + 64 b, + 64)
-  static_assert(D <= 64 && NACC * D == 64, "two O buffers of 64 columns");
+  static constexpr int O_COLS = (D <= 64) ? 64 : D;                 // columns of one O accumulator set
+  static constexpr int NACC = O_COLS / D;                           // independent accumulators per set (summed in the epilogue)
+  static constexpr int TMEM_O = 3 * 128;                            // set b: columns [TMEM_O + O_COLS b, + O_COLS)
+  static_assert(D <= 128 && TMEM_O + NO * O_COLS <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
@@ -558,8 +564,8 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_persist_ker
         for (long long k = blockIdx.x; k < n_items; k += gridDim.x) {
           const FwdItem it = fwd_item(p, k, ntiles);
           if (it.T == 0) continue;
-          const int qb = n & 1;
-          if (n >= 2) mbar_wait(&bars->q_empty[qb], ((n >> 1) - 1) & 1);   // the score GEMMs of item n - 2 have read this buffer
+          const int qb = n % PC::NQ;
+          if (n >= PC::NQ) mbar_wait(&bars->q_empty[qb], ((n / PC::NQ) - 1) & 1);   // the score GEMMs of item n - NQ have read this buffer
           mbar_arrive_expect_tx(&bars->q_full[qb], Cfg::TILE_BYTES);
 #pragma unroll
           for (int bx = 0; bx < Cfg::NBOX; ++bx)
@@ -607,8 +613,8 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_persist_ker
       for (long long k = blockIdx.x; k < n_items; k += gridDim.x) {
         const FwdItem it = fwd_item(p, k, ntiles);
         if (it.T == 0) continue;
-        const int qb = n & 1;
-        mbar_wait(&bars->q_full[qb], (n >> 1) & 1);
+        const int qb = n % PC::NQ;
+        mbar_wait(&bars->q_full[qb], (n / PC::NQ) & 1);
         const uint64_t qd = dq0 + (uint64_t)((qb * Cfg::TILE_BYTES) >> 4);
         for (int i = 0; i < it.T; ++i) {
           const int g = g0 + i, st = g % 3;
@@ -641,9 +647,9 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_persist_ker
       for (long long k = blockIdx.x; k < n_items; k += gridDim.x) {
         const FwdItem it = fwd_item(p, k, ntiles);
         if (it.T == 0) continue;
-        const int ob = n & 1;
-        if (n >= 2) {                                                        // the epilogue of item n - 2 has read this O buffer
-          mbar_wait(&bars->o_empty[ob], ((n >> 1) - 1) & 1);
+        const int ob = n % PC::NO;
+        if (n >= PC::NO) {                                                   // the epilogue of item n - NO has read this O buffer
+          mbar_wait(&bars->o_empty[ob], ((n / PC::NO) - 1) & 1);
           tc_fence_after_sync();
         }
         for (int i = 0; i < it.T; ++i) {
@@ -656,7 +662,7 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_persist_ker
           if (leader) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              mma_ts(tmem + PC::TMEM_O + ob * 64 + (ks % PC::NACC) * D, tp + ks * 8, vd + (uint64_t)((ks * 16 * SW) >> 4), idesc_pv,
+              mma_ts(tmem + PC::TMEM_O + ob * PC::O_COLS + (ks % PC::NACC) * D, tp + ks * 8, vd + (uint64_t)((ks * 16 * SW) >> 4), idesc_pv,
                      (i > 0) || (ks >= PC::NACC));
             mma_commit(&bars->pv_done[st]);
             if (i == it.T - 1) mma_commit(&bars->o_full[ob]);
@@ -749,8 +755,8 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_persist_ker
         mbar_arrive(&bars->p_full[st]);
       }
       // ---------------- epilogue of this item: O buffer n & 1 -> * 1/N -> global; then hand the buffer back ----------------
-      const int ob = n & 1;
-      mbar_wait(&bars->o_full[ob], (n >> 1) & 1);
+      const int ob = n % PC::NO;
+      mbar_wait(&bars->o_full[ob], (n / PC::NO) & 1);
       tc_fence_after_sync();
       constexpr int HALF = D / 2;
       const int cbase = wg * HALF;
@@ -758,12 +764,12 @@ __global__ void __launch_bounds__(BF16 ? 512 : 384, 1) attn_fwd_umma_persist_ker
 #pragma unroll
       for (int c = 0; c < HALF / 16; ++c) {
         uint32_t o[16];
-        tmem_ld16(tmem + PC::TMEM_O + ob * 64 + cbase + c * 16 + lane_bits, o);
+        tmem_ld16(tmem + PC::TMEM_O + ob * PC::O_COLS + cbase + c * 16 + lane_bits, o);
         tmem_ld_wait();
 #pragma unroll
         for (int a = 1; a < PC::NACC; ++a) {
           uint32_t o2[16];
-          tmem_ld16(tmem + PC::TMEM_O + ob * 64 + a * D + cbase + c * 16 + lane_bits, o2);
+          tmem_ld16(tmem + PC::TMEM_O + ob * PC::O_COLS + a * D + cbase + c * 16 + lane_bits, o2);
           tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) + __uint_as_float(o2[e]));
@@ -860,7 +866,7 @@ static int launch_fwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   fp.inv_n = 1.0f / (float)p.max_seq_len;
   fp.heads = p.heads;
   fp.batch = p.batch;
-  if constexpr (D <= 64) {
+  if constexpr (D <= 128) {
     static const int forced = [] { const char* e = getenv("HSTU_FWD_PERSIST"); return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0); }();
     if (forced == 1 || (forced < 0 && p.max_seq_len <= 4096)) return launch_fwd_persist<D, BF16>(fp, p, st);
   }

@@ -18,8 +18,8 @@ _spec.loader.exec_module(_b)
 Bar, Violation, _simulate = _b.Bar, _b.Violation, _b._simulate
 
 
-def run(items, seed, conv=True):
-    """items: list of key-tile counts per work item."""
+def run(items, seed, conv=True, NQ=2, NO=2):
+    """items: list of key-tile counts per work item; NQ Q buffers and NO O accumulator sets (2 / 2 for d <= 64, 1 / 1 for d = 128)."""
     rnd = random.Random(seed)
     B = {}
     for i in range(2):
@@ -40,9 +40,9 @@ def run(items, seed, conv=True):
 
     def KP():
         for g0, n, T in walk():
-            qb = n & 1
-            if n >= 2:
-                yield ("wait", f"qe{qb}", (n >> 1) - 1)
+            qb = n % NQ
+            if n >= NQ:
+                yield ("wait", f"qe{qb}", n // NQ - 1)
             yield ("async", f"qf{qb}")
             for i in range(T):
                 g = g0 + i
@@ -67,7 +67,7 @@ def run(items, seed, conv=True):
 
     def QK():
         for g0, n, T in walk():
-            yield ("wait", f"qf{n & 1}", n >> 1)
+            yield ("wait", f"qf{n % NQ}", n // NQ)
             for i in range(T):
                 g = g0 + i
                 if g >= 3:
@@ -75,19 +75,19 @@ def run(items, seed, conv=True):
                 yield ("wait", f"kf{g % 3}", g // 3)
                 yield ("async", f"sf{g % 3}")
                 if i == T - 1:
-                    yield ("async", f"qe{n & 1}")
+                    yield ("async", f"qe{n % NQ}")
 
     def PV():
         for g0, n, T in walk():
-            if n >= 2:
-                yield ("wait", f"oe{n & 1}", (n >> 1) - 1)
+            if n >= NO:
+                yield ("wait", f"oe{n % NO}", n // NO - 1)
             for i in range(T):
                 g = g0 + i
                 yield ("wait", f"pf{g % 3}", g // 3)
                 yield ("wait", f"{vrdy}{g % 3}", g // 3)
                 yield ("async", f"pd{g % 3}")
                 if i == T - 1:
-                    yield ("async", f"of{n & 1}")
+                    yield ("async", f"of{n % NO}")
 
     def W(w):
         for g0, n, T in walk():
@@ -97,8 +97,8 @@ def run(items, seed, conv=True):
                     continue
                 yield ("wait", f"sf{g % 3}", g // 3)
                 yield ("arrive", f"pf{g % 3}")
-            yield ("wait", f"of{n & 1}", n >> 1)
-            yield ("arrive", f"oe{n & 1}")
+            yield ("wait", f"of{n % NO}", n // NO)
+            yield ("arrive", f"oe{n % NO}")
 
     actors = {"KP": KP(), "VP": VP(), "QK": QK(), "PV": PV(), "W0": W(0), "W1": W(1)}
     if conv:
@@ -120,9 +120,9 @@ if __name__ == "__main__":
     bad = 0
     for items in list(item_lists(rnd, 40)) + [[1] * 9, [4] * 5, [64, 1, 64], [0, 0, 3]]:
         for seed in range(a.seeds // 20):
-            for conv in (True, False):
+            for conv, nq in ((True, 2), (False, 2), (True, 1)):
                 try:
-                    run(items, seed, conv)
+                    run(items, seed, conv, nq, nq)
                 except Violation as e:
                     bad += 1
                     print(items, seed, conv, e)

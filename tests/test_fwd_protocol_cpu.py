@@ -12,10 +12,10 @@ sim = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(sim)
 
 
-@pytest.mark.parametrize("conv", [True, False])
-def test_persistent_forward_protocol(conv):
+@pytest.mark.parametrize("conv,buffers", [(True, 2), (False, 2), (True, 1), (False, 1)])
+def test_persistent_forward_protocol(conv, buffers):
     rnd = random.Random(3)
     lists = list(sim.item_lists(rnd, 30)) + [[1] * 9, [4] * 5, [64, 1, 64], [0, 0, 3], [2], [0]]
     for items in lists:
         for seed in range(8):
-            sim.run(items, seed, conv)
+            sim.run(items, seed, conv, buffers, buffers)
