@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kFwdThreads<D, BF16>, 1) attn_fwd_umma_kernel(
 
 
 // ------------------------------------------------------------------------------------------------
-// Persistent forward (d <= 128, max_seq_len <= 4096): ONE CTA per SM walks a static list of work items (query tile, head, sequence), heavy tiles
+// Persistent forward (d <= 64: max_seq_len <= 4096; d = 128: max_seq_len <= 512): ONE CTA per SM walks a static list of work items (query tile, head, sequence), heavy tiles
 // first.  TMEM is allocated and the barriers are initialised once; the K / V rings, the score slots and the barrier phases run on
 // a GLOBAL key-tile counter, so the loads and score GEMMs of item k + 1 start while item k is still in its silu / P.V / epilogue
 // phase.  Q has two buffers (q_full / q_empty), O two TMEM accumulator sets (o_full / o_empty) for the same reason.  Short sequences
@@ -868,7 +868,10 @@ static int launch_fwd_umma(const hstu_attn_params& p, cudaStream_t st) {
   fp.batch = p.batch;
   if constexpr (D <= 128) {
     static const int forced = [] { const char* e = getenv("HSTU_FWD_PERSIST"); return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0); }();
-    if (forced == 1 || (forced < 0 && p.max_seq_len <= 4096)) return launch_fwd_persist<D, BF16>(fp, p, st);
+    // measured thresholds (profiles/r02_ablations.txt): d <= 64 wins up to Lmax 2048 (3.5 %) and loses 1 % at 8192; d = 128, with
+    // one Q buffer and one O set, wins 12 % at Lmax 512 and loses 20 % at 2048
+    constexpr int kPersistMaxLen = (D <= 64) ? 4096 : 512;
+    if (forced == 1 || (forced < 0 && p.max_seq_len <= kPersistMaxLen)) return launch_fwd_persist<D, BF16>(fp, p, st);
   }
   auto kern = attn_fwd_umma_kernel<D, BF16>;
   HSTU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
