@@ -1,5 +1,7 @@
 // Jagged HSTU attention forward on the 5th-gen tensor cores (tcgen05 + TMEM) with TMA-staged tiles.  bf16 / fp16,
-// dqk == dv in {32, 64, 128}.
+// dqk == dv in {32, 64, 128, 256}.  Two kernels share the roles below: attn_fwd_umma_kernel (one CTA per work item; long sequences)
+// and attn_fwd_umma_persist_kernel (one CTA per SM walking a static item list with all rings / phases on a global key-tile
+// counter; short sequences, see its header further down).
 //
 // One CTA per (128-row query tile, head, sequence); heavy (late) query tiles are scheduled first.  Warp roles:
 //   warp 0  lane 0 : TMA producer for Q (once) and the K tiles (3 stages; stage t % 3 is reused once s_full of tile t
