@@ -1,5 +1,5 @@
-"""The bench.py output contract, checked on the committed result lines of this round (profiles/r01_bench_*.json) and on the
-helpers that do not need a GPU."""
+"""The bench.py output contract, checked on the committed result lines (profiles/r01_bench_*.json, profiles/r02_bench_*.json) and on
+the helpers that do not need a GPU."""
 import importlib.util
 import json
 import os
@@ -52,3 +52,28 @@ def test_traffic_is_reported_only_for_the_captured_shape():
     assert got == t["kernels"]["attn_bwd"]["dram_bytes"] and "ncu_traffic.json" in src
     other = dict(t["attn_shape"], d=t["attn_shape"]["d"] * 2)
     assert b.ncu_traffic({"attn_shape": other}) == (None, None)
+
+
+def test_round2_lines():
+    one, two, strong = _load("r02_bench_1gpu.json"), _load("r02_bench_2gpu.json"), _load("r02_bench_2gpu_strong.json")
+    for d, n, scaling in ((one, 1, "weak"), (two, 2, "weak"), (strong, 2, "strong")):
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+            assert k in d, k
+        assert d["n_gpus"] == n and d["scaling"] == scaling and d["warmup"] >= 3
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+        assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # the CPU arm of round 2 times the reference's own eager code (oracle/_ref recipe), not the port
+    assert one["cpu_baseline"]["kind"] == "reference"
+    # weak scaling keeps the per-GPU work: two GPUs process twice the sequences in (almost) the same step time
+    assert two["config"]["global_batch"] == 2 * one["config"]["global_batch"]
+    assert two["ms_per_step"] < 1.1 * one["ms_per_step"]
+    # strong scaling keeps the global batch
+    assert strong["config"]["global_batch"] == one["config"]["global_batch"]
+    ref = _load("r02_bench_reference_arm.json")
+    assert ref["impl"] == "reference" and ref["cpu_baseline"]["kind"] == "reference"
+    assert ref["e2e"]["value"] == ref["value"] == ref["cpu_baseline"]["value"]
+    for line in open(os.path.join(ROOT, "profiles", "r02_bench_research.json")):
+        d = json.loads(line)
+        assert d["unit"] == "sequences/s" and d["value"] > 0 and "research" in d["metric"]
